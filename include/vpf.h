@@ -1,0 +1,95 @@
+/*
+ * vpf.h -- C ABI of libvpf_b200.so, the B200 (sm_100a) implementation of the
+ * ViPFormer pre-training hot path.
+ *
+ * The reference has no FFI: its boundary is a set of Python callables
+ * (SURVEY.md section 8b).  Each entry below names the reference callable it
+ * sits under (paths relative to the upstream repo root); the Python mirror in
+ * vipformer_b200/ binds these with ctypes and keeps the reference signatures.
+ *
+ * Conventions (every entry):
+ *   - plain pointers + sizes, no torch / C++ types;
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - row-major, contiguous; fp32 = float, bf16 = uint16_t storage,
+ *     indices int64_t (what the reference returns);
+ *   - `stream` is a cudaStream_t passed as void*; entries enqueue work on it
+ *     and return without synchronising; they never allocate device memory
+ *     (scratch is caller-provided through the *_workspace_bytes queries);
+ *   - return 0 on success, a negative VPF_E* code otherwise;
+ *     vpf_last_error_string() describes the last failure on this host thread;
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef VPF_H_
+#define VPF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPF_OK 0
+#define VPF_EINVAL (-1)      /* bad argument / unsupported shape */
+#define VPF_ECUDA (-2)       /* a CUDA runtime / driver call failed */
+#define VPF_EWORKSPACE (-3)  /* workspace too small */
+
+#define VPF_ABI_VERSION 1
+
+int vpf_abi_version(void);
+const char *vpf_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches` claim is read from here). */
+int64_t vpf_launch_count(void);
+void vpf_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ tokenizer
+ * vipformer/model/pointcloud/utils.py */
+
+/* farthest_point_sample, utils.py:56-85.  pts [B,N,C] fp32 (C>=3, channels
+ * 0..2 used), start_idx [B] int64 (replaces the torch.randint draw of
+ * utils.py:71), out_idx [B,npoint] int64.  Tie-break: lowest index.
+ * Limits: 1 <= N <= 8192. */
+int vpf_fps(const float *pts, int B, int N, int C, int npoint,
+            const int64_t *start_idx, int64_t *out_idx, void *stream);
+
+/* index_points, utils.py:88-104.  out[b,s,:] = points[b, idx[b,s], :]. */
+int vpf_index_points(const float *points, int B, int N, int C,
+                     const int64_t *idx, int S, float *out, void *stream);
+
+/* square_distance, utils.py:122-141.  src [B,S,Cs], dst [B,N,Cd] (first three
+ * channels), out [B,S,N] fp32, arithmetic pinned as in oracle/tokenizer_oracle.c */
+int vpf_square_distance(const float *src, int B, int S, int Cs,
+                        const float *dst, int N, int Cd, float *out,
+                        void *stream);
+
+/* knn_point, utils.py:107-119.  xyz [B,N,C], new_xyz [B,S,Cq] -> out_idx
+ * [B,S,nsample] int64: the nsample smallest by (distance asc, index asc), in
+ * that order.  Limits: nsample <= 32, nsample <= N <= 8192. */
+int vpf_knn_point(int nsample, const float *xyz, int B, int N, int C,
+                  const float *new_xyz, int S, int Cq, int64_t *out_idx,
+                  void *stream);
+
+/* divide_patches, utils.py:6-38 (FPS -> kNN -> gather -> slot-0..2 centre
+ * subtraction, utils.py:36).  neighbors [B,G,S,C], centers [B,G,C];
+ * fps_idx [B,G] / knn_idx [B,G,S] int64 are optional outputs (NULL to skip).
+ * Limits: S <= 32, S <= N <= 8192, C >= 3. */
+int vpf_divide_patches(const float *pts, int B, int N, int C, int G, int S,
+                       const int64_t *start_idx, float *neighbors,
+                       float *centers, int64_t *fps_idx, int64_t *knn_idx,
+                       void *stream);
+
+/* Same, HOST buffers in and out (pinned or pageable): H2D copy, the two
+ * kernels, D2H copy, stream-synchronised before returning.  `workspace` is a
+ * DEVICE scratch of at least vpf_divide_patches_host_workspace_bytes(). */
+size_t vpf_divide_patches_host_workspace_bytes(int B, int N, int C, int G, int S);
+int vpf_divide_patches_host(const float *pts_host, int B, int N, int C, int G,
+                            int S, const int64_t *start_idx_host,
+                            float *neighbors_host, float *centers_host,
+                            void *workspace, size_t workspace_bytes,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPF_H_ */

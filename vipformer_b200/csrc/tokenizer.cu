@@ -1,0 +1,332 @@
+// tokenizer.cu -- point-cloud tokenizer kernels for sm_100a.
+//
+//   K1 fps_kernel        farthest-point sampling, one CTA per cloud, the cloud
+//                        resident in registers (running distance) and shared
+//                        memory (centroid lookup); argmax by two redux.sync
+//                        per level, one __syncthreads per iteration.
+//   K2 knn_group_kernel  kNN selection (warp-per-query streaming top-32 over a
+//                        shared-memory copy of the cloud) fused with the patch
+//                        gather and the reference's slot-0..2 centre
+//                        subtraction; the [B,G,N] distance matrix the reference
+//                        materialises never exists.
+//
+// Reference: vipformer/model/pointcloud/utils.py:6-141.  Arithmetic is pinned
+// exactly as oracle/tokenizer_oracle.c states it (explicit __fmul_rn/__fadd_rn
+// where the reference does not fuse, fmaf where it does), so indices are
+// bit-exact with the oracle, including under ties (lowest index wins).
+#include "common.cuh"
+
+namespace vpf {
+
+constexpr int kFpsThreads = 256;
+constexpr int kKnnThreads = 256;
+constexpr int kMaxPoints = 8192;
+constexpr unsigned kFull = 0xffffffffu;
+
+// monotone float -> uint32 map (handles the slightly negative distances the
+// expanded form produces)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------- K1: FPS ---
+// utils.py:56-85.  PPT = points per thread (N <= PPT * kFpsThreads).
+template <int PPT>
+__global__ void __launch_bounds__(kFpsThreads)
+fps_kernel(const float *__restrict__ pts, int N, int C, int npoint,
+           const int64_t *__restrict__ start_idx, int64_t *__restrict__ out_idx,
+           float *__restrict__ centers) {
+  extern __shared__ float s_xyz[];  // [N*3] AoS copy of the cloud's coordinates
+  __shared__ uint32_t s_val[2][kFpsThreads / 32];
+  __shared__ uint32_t s_idx[2][kFpsThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float *p = pts + (size_t)b * N * C;
+
+  if (C == 3) {
+    for (int i = tid; i < N * 3; i += kFpsThreads) s_xyz[i] = p[i];  // coalesced
+  } else {
+    for (int i = tid; i < N * 3; i += kFpsThreads) s_xyz[i] = p[(size_t)(i / 3) * C + (i % 3)];
+  }
+  __syncthreads();
+
+  float x[PPT], y[PPT], z[PPT], run[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int i = tid + k * kFpsThreads;
+    const bool ok = i < N;
+    x[k] = ok ? s_xyz[3 * i + 0] : 0.f;
+    y[k] = ok ? s_xyz[3 * i + 1] : 0.f;
+    z[k] = ok ? s_xyz[3 * i + 2] : 0.f;
+    run[k] = ok ? 1e10f : -1.0f;  // utils.py:69; padding can never win
+  }
+
+  long long st = start_idx[b];
+  int far = (int)(st < 0 ? 0 : (st >= N ? N - 1 : st));
+
+  for (int it = 0; it < npoint; ++it) {
+    if (tid == 0 && out_idx) out_idx[(size_t)b * npoint + it] = far;  // utils.py:75
+    if (centers && tid < C) centers[((size_t)b * npoint + it) * C + tid] = p[(size_t)far * C + tid];
+    const float cx = s_xyz[3 * far + 0], cy = s_xyz[3 * far + 1], cz = s_xyz[3 * far + 2];
+    float best = -1.0f;
+    int besti = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const float dx = __fsub_rn(x[k], cx), dy = __fsub_rn(y[k], cy), dz = __fsub_rn(z[k], cz);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // utils.py:79
+      const float r = fminf(run[k], d);                                                                 // utils.py:81
+      run[k] = r;
+      if (r > best) { best = r; besti = tid + k * kFpsThreads; }  // ascending index => strict > keeps the lowest
+    }
+    // argmax across the CTA (utils.py:83): max value, then min index among the maxima
+    const uint32_t key = best < 0.f ? 0u : __float_as_uint(best) + 1u;  // run >= +0 => bits monotone
+    const uint32_t wmax = __reduce_max_sync(kFull, key);
+    const uint32_t wi = __reduce_min_sync(kFull, key == wmax ? (uint32_t)besti : 0xffffffffu);
+    const int buf = it & 1;
+    if (lane == 0) { s_val[buf][warp] = wmax; s_idx[buf][warp] = wi; }
+    __syncthreads();
+    const uint32_t v = lane < kFpsThreads / 32 ? s_val[buf][lane] : 0u;
+    const uint32_t vi = lane < kFpsThreads / 32 ? s_idx[buf][lane] : 0xffffffffu;
+    const uint32_t m = __reduce_max_sync(kFull, v);
+    far = (int)__reduce_min_sync(kFull, v == m ? vi : 0xffffffffu);
+  }
+}
+
+// ------------------------------------------------- K2: kNN + gather (fused) ---
+// utils.py:107-141 (selection) and utils.py:22-36 (gather + slot quirk).
+// grid = (B, splits); warp w of split y handles queries q = y*per + w, +8, ...
+__global__ void __launch_bounds__(kKnnThreads)
+knn_group_kernel(const float *__restrict__ pts, int N, int C,
+                 const float *__restrict__ queries, int Q, int Cq, int nsample,
+                 int q_per_cta, int64_t *__restrict__ knn_idx,
+                 float *__restrict__ neighbors) {
+  extern __shared__ float4 s_pt[];  // [N] (x, y, z, |p|^2)
+  __shared__ float s_out[kKnnThreads / 32][32 * 3];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float *p = pts + (size_t)b * N * C;
+  for (int i = tid; i < N; i += kKnnThreads) {
+    const float x = p[(size_t)i * C + 0], y = p[(size_t)i * C + 1], z = p[(size_t)i * C + 2];
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));  // utils.py:140
+    s_pt[i] = make_float4(x, y, z, n2);
+  }
+  __syncthreads();
+
+  const int q_begin = blockIdx.y * q_per_cta;
+  const int q_end = min(Q, q_begin + q_per_cta);
+  const uint32_t kEmptyHi = 0xff800000u;  // f2ord(+inf)
+
+  for (int q = q_begin + warp; q < q_end; q += kKnnThreads / 32) {
+    const float *c = queries + ((size_t)b * Q + q) * Cq;
+    const float cx = c[0], cy = c[1], cz = c[2];
+    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));  // utils.py:139
+    uint32_t Lhi = kEmptyHi, Llo = 0xffffffffu;  // lane l holds the l-th smallest key so far
+    float worst = __int_as_float(0x7f800000);
+
+    for (int base = 0; base < N; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < N;
+      const float4 P = s_pt[valid ? i : 0];
+      const float dot = fmaf(cz, P.z, fmaf(cy, P.y, __fmul_rn(cx, P.x)));           // utils.py:138
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), c2), P.w);         // utils.py:138-140
+      unsigned mask = __ballot_sync(kFull, valid && d <= worst);
+      if (mask) {
+        const uint32_t khi = f2ord(d), klo = (uint32_t)i;
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t h = __shfl_sync(kFull, khi, src), l = __shfl_sync(kFull, klo, src);
+          const bool less = (Lhi < h) || (Lhi == h && Llo < l);
+          const int pos = __popc(__ballot_sync(kFull, less));
+          if (pos < nsample) {
+            const uint32_t uhi = __shfl_up_sync(kFull, Lhi, 1), ulo = __shfl_up_sync(kFull, Llo, 1);
+            if (lane == pos) { Lhi = h; Llo = l; }
+            else if (lane > pos) { Lhi = uhi; Llo = ulo; }
+          }
+        }
+        worst = ord2f(__shfl_sync(kFull, Lhi, nsample - 1));
+      }
+    }
+
+    const size_t row = (size_t)b * Q + q;
+    if (knn_idx && lane < nsample) knn_idx[row * nsample + lane] = (int64_t)Llo;
+    if (neighbors) {
+      if (C == 3) {
+        if (lane < nsample) {
+          const float4 P = s_pt[Llo];
+          const bool sub = lane < 3;  // utils.py:36 slices the SLOT axis: only slots 0,1,2 are centred
+          s_out[warp][lane * 3 + 0] = sub ? __fsub_rn(P.x, cx) : P.x;
+          s_out[warp][lane * 3 + 1] = sub ? __fsub_rn(P.y, cy) : P.y;
+          s_out[warp][lane * 3 + 2] = sub ? __fsub_rn(P.z, cz) : P.z;
+        }
+        __syncwarp();
+        float *o = neighbors + row * nsample * 3;
+        for (int t = lane; t < nsample * 3; t += 32) o[t] = s_out[warp][t];  // coalesced
+        __syncwarp();
+      } else {
+        float *o = neighbors + row * nsample * C;
+        for (int t0 = 0; t0 < nsample * C; t0 += 32) {
+          const int t = t0 + lane;
+          const int s = min(t / C, nsample - 1), ch = t % C;
+          const uint32_t j = __shfl_sync(kFull, Llo, s);
+          if (t < nsample * C) {
+            float v = p[(size_t)j * C + ch];
+            if (s < 3) v = __fsub_rn(v, c[ch]);
+            o[t] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// utils.py:122-141, materialised (API parity only; the fused path never calls it)
+__global__ void square_distance_kernel(const float *__restrict__ src, int S, int Cs,
+                                       const float *__restrict__ dst, int N, int Cd,
+                                       float *__restrict__ out) {
+  const int b = blockIdx.z, s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float *c = src + ((size_t)b * S + s) * Cs;
+  const float *p = dst + ((size_t)b * N + i) * Cd;
+  const float cx = c[0], cy = c[1], cz = c[2], x = p[0], y = p[1], z = p[2];
+  const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+  const float p2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  const float dot = fmaf(cz, z, fmaf(cy, y, __fmul_rn(cx, x)));
+  out[((size_t)b * S + s) * N + i] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), c2), p2);
+}
+
+// utils.py:88-104
+__global__ void index_points_kernel(const float *__restrict__ points, int N, int C,
+                                    const int64_t *__restrict__ idx, int S, float *__restrict__ out,
+                                    size_t total) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int ch = (int)(t % C);
+  const size_t bs = t / C;
+  const size_t b = bs / S;
+  long long j = idx[bs];
+  j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+  out[t] = points[(b * N + (size_t)j) * C + ch];
+}
+
+// ------------------------------------------------------------ host launchers
+static int launch_fps(const float *pts, int B, int N, int C, int npoint, const int64_t *start,
+                      int64_t *out_idx, float *centers, cudaStream_t st) {
+  if (B == 0 || npoint == 0) return VPF_OK;
+  const size_t smem = (size_t)N * 3 * sizeof(float);
+#define VPF_FPS_CASE(PPT)                                                                         \
+  if (N <= PPT * kFpsThreads) {                                                                   \
+    if (smem > 48 * 1024)                                                                         \
+      VPF_CUDA_TRY(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    fps_kernel<PPT><<<B, kFpsThreads, smem, st>>>(pts, N, C, npoint, start, out_idx, centers);    \
+    return check_launch("fps_kernel");                                                            \
+  }
+  VPF_FPS_CASE(1) VPF_FPS_CASE(2) VPF_FPS_CASE(4) VPF_FPS_CASE(8) VPF_FPS_CASE(10) VPF_FPS_CASE(16) VPF_FPS_CASE(32)
+#undef VPF_FPS_CASE
+  return fail(VPF_EINVAL, "fps: N=%d exceeds the supported maximum %d", N, kMaxPoints);
+}
+
+static int launch_knn(const float *pts, int B, int N, int C, const float *queries, int Q, int Cq,
+                      int nsample, int64_t *knn_idx, float *neighbors, cudaStream_t st) {
+  if (B == 0 || Q == 0) return VPF_OK;
+  const size_t smem = (size_t)N * sizeof(float4);
+  if (smem > 48 * 1024)
+    VPF_CUDA_TRY(cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // enough CTAs for >= 2 waves on small batches; a split re-stages the cloud (cheap)
+  const int warps = kKnnThreads / 32;
+  int splits = ceil_div(2 * num_sms() * 4, B);
+  splits = max(1, min(splits, ceil_div(Q, warps)));
+  const int per = ceil_div(ceil_div(Q, splits), warps) * warps;
+  splits = ceil_div(Q, per);
+  knn_group_kernel<<<dim3(B, splits), kKnnThreads, smem, st>>>(pts, N, C, queries, Q, Cq, nsample, per,
+                                                               knn_idx, neighbors);
+  return check_launch("knn_group_kernel");
+}
+
+}  // namespace vpf
+
+using namespace vpf;
+
+extern "C" {
+
+int vpf_fps(const float *pts, int B, int N, int C, int npoint, const int64_t *start_idx,
+            int64_t *out_idx, void *stream) {
+  VPF_REQUIRE(pts && start_idx && out_idx, "fps: null pointer");
+  VPF_REQUIRE(B >= 0 && N >= 1 && N <= kMaxPoints && C >= 3 && npoint >= 0, "fps: bad shape B=%d N=%d C=%d npoint=%d", B, N, C, npoint);
+  return launch_fps(pts, B, N, C, npoint, start_idx, out_idx, nullptr, (cudaStream_t)stream);
+}
+
+int vpf_index_points(const float *points, int B, int N, int C, const int64_t *idx, int S, float *out,
+                     void *stream) {
+  VPF_REQUIRE(points && idx && out, "index_points: null pointer");
+  VPF_REQUIRE(B >= 0 && N >= 1 && C >= 1 && S >= 0, "index_points: bad shape");
+  const size_t total = (size_t)B * S * C;
+  if (total == 0) return VPF_OK;
+  index_points_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, (cudaStream_t)stream>>>(points, N, C, idx, S, out, total);
+  return check_launch("index_points_kernel");
+}
+
+int vpf_square_distance(const float *src, int B, int S, int Cs, const float *dst, int N, int Cd,
+                        float *out, void *stream) {
+  VPF_REQUIRE(src && dst && out, "square_distance: null pointer");
+  VPF_REQUIRE(B >= 0 && S >= 0 && N >= 0 && Cs >= 3 && Cd >= 3 && S <= 65535 && B <= 65535, "square_distance: bad shape");
+  if (B == 0 || S == 0 || N == 0) return VPF_OK;
+  square_distance_kernel<<<dim3(ceil_div(N, 256), S, B), 256, 0, (cudaStream_t)stream>>>(src, S, Cs, dst, N, Cd, out);
+  return check_launch("square_distance_kernel");
+}
+
+int vpf_knn_point(int nsample, const float *xyz, int B, int N, int C, const float *new_xyz, int S,
+                  int Cq, int64_t *out_idx, void *stream) {
+  VPF_REQUIRE(xyz && new_xyz && out_idx, "knn_point: null pointer");
+  VPF_REQUIRE(nsample >= 1 && nsample <= 32, "knn_point: nsample=%d unsupported (1..32)", nsample);
+  VPF_REQUIRE(B >= 0 && N >= nsample && N <= kMaxPoints && C >= 3 && Cq >= 3 && S >= 0, "knn_point: bad shape B=%d N=%d C=%d S=%d (need nsample <= N <= %d)", B, N, C, S, kMaxPoints);
+  return launch_knn(xyz, B, N, C, new_xyz, S, Cq, nsample, out_idx, nullptr, (cudaStream_t)stream);
+}
+
+int vpf_divide_patches(const float *pts, int B, int N, int C, int G, int S, const int64_t *start_idx,
+                       float *neighbors, float *centers, int64_t *fps_idx, int64_t *knn_idx, void *stream) {
+  VPF_REQUIRE(pts && start_idx && neighbors && centers, "divide_patches: null pointer");
+  VPF_REQUIRE(S >= 1 && S <= 32, "divide_patches: group_size=%d unsupported (1..32)", S);
+  VPF_REQUIRE(B >= 0 && N >= S && N <= kMaxPoints && C >= 3 && G >= 0, "divide_patches: bad shape B=%d N=%d C=%d G=%d S=%d (need S <= N <= %d)", B, N, C, G, S, kMaxPoints);
+  cudaStream_t st = (cudaStream_t)stream;
+  VPF_TRY(launch_fps(pts, B, N, C, G, start_idx, fps_idx, centers, st));
+  return launch_knn(pts, B, N, C, centers, G, C, S, knn_idx, neighbors, st);
+}
+
+size_t vpf_divide_patches_host_workspace_bytes(int B, int N, int C, int G, int S) {
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  return al((size_t)B * N * C * 4) + al((size_t)B * 8) + al((size_t)B * G * S * C * 4) + al((size_t)B * G * C * 4);
+}
+
+int vpf_divide_patches_host(const float *pts_host, int B, int N, int C, int G, int S,
+                            const int64_t *start_idx_host, float *neighbors_host, float *centers_host,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+  VPF_REQUIRE(pts_host && start_idx_host && neighbors_host && centers_host && workspace, "divide_patches_host: null pointer");
+  if (workspace_bytes < vpf_divide_patches_host_workspace_bytes(B, N, C, G, S))
+    return fail(VPF_EWORKSPACE, "divide_patches_host: workspace %zu < %zu bytes", workspace_bytes,
+                vpf_divide_patches_host_workspace_bytes(B, N, C, G, S));
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  cudaStream_t st = (cudaStream_t)stream;
+  char *w = (char *)workspace;
+  float *d_pts = (float *)w; w += al((size_t)B * N * C * 4);
+  int64_t *d_start = (int64_t *)w; w += al((size_t)B * 8);
+  float *d_nb = (float *)w; w += al((size_t)B * G * S * C * 4);
+  float *d_ce = (float *)w;
+  VPF_CUDA_TRY(cudaMemcpyAsync(d_pts, pts_host, (size_t)B * N * C * 4, cudaMemcpyHostToDevice, st));
+  VPF_CUDA_TRY(cudaMemcpyAsync(d_start, start_idx_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  VPF_TRY(vpf_divide_patches(d_pts, B, N, C, G, S, d_start, d_nb, d_ce, nullptr, nullptr, stream));
+  VPF_CUDA_TRY(cudaMemcpyAsync(neighbors_host, d_nb, (size_t)B * G * S * C * 4, cudaMemcpyDeviceToHost, st));
+  VPF_CUDA_TRY(cudaMemcpyAsync(centers_host, d_ce, (size_t)B * G * C * 4, cudaMemcpyDeviceToHost, st));
+  VPF_CUDA_TRY(cudaStreamSynchronize(st));
+  return VPF_OK;
+}
+
+}  // extern "C"
