@@ -89,6 +89,53 @@ int vpf_divide_patches_host(const float *pts_host, int B, int N, int C, int G,
                             void *workspace, size_t workspace_bytes,
                             void *stream);
 
+
+/* ------------------------------------------------------------ dense contraction
+ * One tcgen05/TMA GEMM serves every Linear / 1x1-Conv1d on the path, forward and
+ * backward (vipformer/model/pointcloud/partseg.py:46-49,191-198 Linear layers;
+ * utils.py:153-165 Conv1d(k=1); classifier.py:31-36).
+ *
+ *   C[M,N] (op)= epilogue( alpha * sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulate
+ *
+ * a_mn = 0: A is row-major [M][K] (row stride lda elements);  a_mn = 1: A is [K][M].
+ * b_mn = 0: B is row-major [N][K] (row stride ldb elements);  b_mn = 1: B is [K][N].
+ * splits: split-K factor (only with VPF_EPI_ATOMIC_ADD); 0 = choose automatically.
+ * Operand base pointers must be 16-byte aligned, lda/ldb multiples of 8. */
+#define VPF_EPI_STORE 0       /* out = f(acc)                         (bf16 or fp32)       */
+#define VPF_EPI_RESIDUAL 1    /* out_f32 = resid + dropout(f(acc))    (Residual, partseg.py:201-213) */
+#define VPF_EPI_ATOMIC_ADD 2  /* out_f32 += f(acc)  (red.global.add)  weight gradients     */
+#define VPF_ACT_NONE 0
+#define VPF_ACT_RELU 1
+#define VPF_ACT_GELU 2        /* exact erf GELU (nn.GELU default) */
+#define VPF_AUX_NONE 0
+#define VPF_AUX_GELU_GRAD 1   /* f *= gelu'(aux)    (aux = saved pre-activation, bf16)      */
+#define VPF_AUX_RELU_MASK 2   /* f  = aux > 0 ? f : 0                                       */
+
+typedef struct vpf_gemm_epilogue {
+  int mode;               /* VPF_EPI_* */
+  int out_f32;            /* VPF_EPI_STORE: 1 = fp32 output, 0 = bf16 */
+  int ldc;                /* row stride (elements) of out / out2 / resid / out_bf16 */
+  int act;                /* VPF_ACT_* applied after bias */
+  int aux_mode;           /* VPF_AUX_* applied after act */
+  int ld_aux;
+  int rg_shift, rg_ld;    /* row-group bias: rg_bias[(row >> rg_shift) * rg_ld + col] */
+  unsigned int op_id;     /* dropout stream id */
+  float alpha;            /* scale on the accumulator */
+  float drop_p;           /* VPF_EPI_RESIDUAL: dropout probability (0 = off) */
+  void *out;
+  void *out2;             /* optional bf16 copy of (alpha*acc + biases) BEFORE act (saved for backward) */
+  void *out_bf16;         /* VPF_EPI_RESIDUAL: optional bf16 copy of the result */
+  const float *bias;      /* optional [N] */
+  const float *rg_bias;   /* optional [(M >> rg_shift), rg_ld] */
+  const void *aux;        /* optional bf16 [M, ld_aux] */
+  const float *resid;     /* VPF_EPI_RESIDUAL: fp32 [M, ldc] */
+  const unsigned long long *seed_ptr; /* device pointer to the step's dropout seed */
+} vpf_gemm_epilogue;
+
+int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb,
+                  int M, int N, int K, int splits, const vpf_gemm_epilogue *epi,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

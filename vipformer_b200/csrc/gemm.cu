@@ -1,0 +1,356 @@
+// gemm.cu -- the dense-contraction workhorse: bf16 x bf16 -> fp32 on tcgen05.
+//
+//   C[M,N] (op)= epilogue( alpha * sum_k A(m,k) * B(n,k) )
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 6-stage ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128 N=128 K=16; accumulators in TMEM,
+//                               two 128-column accumulator stages so the epilogue of tile i
+//                               overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// Both operands may be K-major (row-major [rows][K]) or MN-major ([K][rows]); that covers the
+// forward (X.W^T), the data gradient (dY.W) and the weight gradient (dY^T.X, split-K with
+// red.global.add.v4.f32) of every Linear / 1x1-Conv on the ViPFormer hot path
+// (vipformer/model/pointcloud/partseg.py:15-198, utils.py:144-189, classifier.py:25-50)
+// without materialising a single transpose.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace vpf {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 6;
+constexpr int kTileBytesA = BM * BK * 2, kTileBytesB = BN * BK * 2;
+constexpr int kStageBytes = kTileBytesA + kTileBytesB;
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTmemCols = 2 * BN;
+
+struct GemmArgs {
+  int M, N, K;
+  int a_mn, b_mn;
+  int num_m_tiles, num_n_tiles, kblocks, kblocks_per_split, splits;
+  vpf_gemm_epilogue e;
+};
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+  uint64_t *empty_bar = full_bar + kStages;
+  uint64_t *tmem_full = empty_bar + kStages;
+  uint64_t *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = g.num_m_tiles * g.num_n_tiles * g.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int n_tile = w % g.num_n_tiles;
+      const int t = w / g.num_n_tiles;
+      const int m_tile = t % g.num_m_tiles;
+      const int split = t / g.num_m_tiles;
+      const int kb0 = split * g.kblocks_per_split, kb1 = min(kb0 + g.kblocks_per_split, g.kblocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t *sa = smem + stage * kStageBytes, *sb = sa + kTileBytesA;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          if (!g.a_mn) {
+            ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
+          } else {
+            ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], m_tile * BM, kb * BK);
+            ptx::tma_load_2d(sa + kTileBytesA / 2, &tma_a, &full_bar[stage], m_tile * BM + 64, kb * BK);
+          }
+          if (!g.b_mn) {
+            ptx::tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+            ptx::tma_load_2d(sb, &tma_b, &full_bar[stage], n_tile * BN, kb * BK);
+            ptx::tma_load_2d(sb + kTileBytesB / 2, &tma_b, &full_bar[stage], n_tile * BN + 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+    // K-major tile: rows of 128 B, 8-row swizzle atoms 1024 B apart; one UMMA_K (16 bf16) = +32 B.
+    // MN-major tile: two 64-wide blocks 8 KB apart (LBO), 8-k-row groups 1024 B apart (SBO);
+    //                one UMMA_K = 16 k-rows = +2048 B.
+    const uint32_t a_lbo = g.a_mn ? kTileBytesA / 2 : 16, b_lbo = g.b_mn ? kTileBytesB / 2 : 16;
+    const uint32_t a_adv = g.a_mn ? 2048 : 32, b_adv = g.b_mn ? 2048 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++iter) {
+      const int split = (w / g.num_n_tiles) / g.num_m_tiles;
+      const int kb0 = split * g.kblocks_per_split, kb1 = min(kb0 + g.kblocks_per_split, g.kblocks);
+      const int acc = iter & 1;
+      ptx::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes), sb = sa + kTileBytesA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = ptx::umma_smem_desc(sa + k * a_adv, a_lbo, 1024);
+            const uint64_t bdesc = ptx::umma_smem_desc(sb + k * b_adv, b_lbo, 1024);
+            ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);                    // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const vpf_gemm_epilogue &e = g.e;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t drop_thr = 0;
+    uint32_t drop_key = 0;
+    float drop_scale = 1.f;
+    if (e.mode == VPF_EPI_RESIDUAL && e.drop_p > 0.f) {
+      drop_thr = rng::threshold(e.drop_p);
+      drop_key = rng::make_key(e.seed_ptr ? *e.seed_ptr : 0ull, e.op_id);
+      drop_scale = 1.f / (1.f - e.drop_p);
+    }
+    int iter = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++iter) {
+      const int n_tile = w % g.num_n_tiles;
+      const int m_tile = (w / g.num_n_tiles) % g.num_m_tiles;
+      const int acc = iter & 1;
+      ptx::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
+      ptx::tc_fence_after();
+      const long long grow = (long long)m_tile * BM + row_in_tile;
+      const bool row_ok = grow < g.M;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n_tile * BN + c;
+        if (!row_ok || col0 >= g.N) continue;
+        const int ncols = min(32, g.N - col0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
+        if (e.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(e.bias + col0 + j);
+        }
+        if (e.rg_bias) {
+          const float *rb = e.rg_bias + (size_t)(grow >> e.rg_shift) * e.rg_ld + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(rb + j);
+        }
+        if (e.out2) {  // pre-activation copy (bf16) for the backward pass
+          __nv_bfloat16 *o2 = reinterpret_cast<__nv_bfloat16 *>(e.out2) + (size_t)grow * e.ldc + col0;
+          if (ncols == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
+              *reinterpret_cast<uint4 *>(o2 + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) o2[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (e.act == VPF_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (e.act == VPF_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+        }
+        if (e.aux_mode != VPF_AUX_NONE) {
+          const __nv_bfloat16 *ax = reinterpret_cast<const __nv_bfloat16 *>(e.aux) + (size_t)grow * e.ld_aux + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              const float a = __bfloat162float(ax[j]);
+              v[j] = e.aux_mode == VPF_AUX_GELU_GRAD ? v[j] * gelu_grad_f(a) : (a > 0.f ? v[j] : 0.f);
+            }
+          }
+        }
+        if (e.mode == VPF_EPI_STORE) {
+          if (e.out_f32) {
+            float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < ncols; ++j) o[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(e.out) + (size_t)grow * e.ldc + col0;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
+                *reinterpret_cast<uint4 *>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16(v[j]);
+            }
+          }
+        } else if (e.mode == VPF_EPI_RESIDUAL) {
+          // out_f32 = resid + dropout(v)     (partseg.py:208-213 Residual)
+          const float *rs = e.resid + (size_t)grow * e.ldc + col0;
+          float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
+          __nv_bfloat16 *ob = e.out_bf16 ? reinterpret_cast<__nv_bfloat16 *>(e.out_bf16) + (size_t)grow * e.ldc + col0 : nullptr;
+          const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              float y = v[j];
+              if (drop_thr) y = rng::keep(drop_key, ebase + j, drop_thr) ? y * drop_scale : 0.f;
+              const float s = rs[j] + y;
+              o[j] = s;
+              if (ob) ob[j] = __float2bfloat16(s);
+            }
+          }
+        } else {  // VPF_EPI_ATOMIC_ADD: split-K weight gradients accumulate into the flat fp32 grad buffer
+          float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
+          if (ncols == 32 && (e.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) ptx::red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < ncols; ++j) atomicAdd(o + j, v[j]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map: array [outer][inner] with row stride ld elements, box {box_inner, box_outer}, 128B swizzle
+int make_tmap_bf16(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VPF_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
+    return fail(VPF_EINVAL, "gemm operand must be 16-byte aligned with a 16-byte-multiple row stride (ld=%llu)", (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VPF_ECUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return VPF_OK;
+}
+
+}  // namespace vpf
+
+using namespace vpf;
+
+extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb, int M, int N, int K,
+                             int splits, const vpf_gemm_epilogue *epi, void *stream) {
+  VPF_REQUIRE(A && B && epi && epi->out, "gemm: null pointer");
+  VPF_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  VPF_REQUIRE(epi->mode == VPF_EPI_STORE || epi->mode == VPF_EPI_RESIDUAL || epi->mode == VPF_EPI_ATOMIC_ADD, "gemm: bad epilogue mode %d", epi->mode);
+  VPF_REQUIRE(epi->mode != VPF_EPI_RESIDUAL || epi->resid, "gemm: residual epilogue needs resid");
+  VPF_REQUIRE(splits == 1 || epi->mode == VPF_EPI_ATOMIC_ADD, "gemm: split-K needs the atomic-add epilogue");
+  VPF_REQUIRE((size_t)M * (size_t)N < (1ull << 32) || epi->drop_p == 0.f, "gemm: dropout index space exceeds 2^32");
+  if (M == 0 || N == 0) return VPF_OK;
+  CUtensorMap ta, tb;
+  if (!a_mn) VPF_TRY(make_tmap_bf16(&ta, A, K, M, lda, BK, BM));
+  else VPF_TRY(make_tmap_bf16(&ta, A, M, K, lda, 64, BK));
+  if (!b_mn) VPF_TRY(make_tmap_bf16(&tb, B, K, N, ldb, BK, BN));
+  else VPF_TRY(make_tmap_bf16(&tb, B, N, K, ldb, 64, BK));
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
+  g.num_m_tiles = ceil_div(M, BM);
+  g.num_n_tiles = ceil_div(N, BN);
+  g.kblocks = ceil_div(K, BK);
+  if (splits < 1) {  // auto: fill the machine
+    const int tiles = g.num_m_tiles * g.num_n_tiles;
+    splits = epi->mode == VPF_EPI_ATOMIC_ADD ? max(1, min(g.kblocks, (2 * num_sms()) / max(1, tiles))) : 1;
+  }
+  g.kblocks_per_split = ceil_div(g.kblocks, splits);
+  g.splits = ceil_div(g.kblocks, g.kblocks_per_split);
+  g.e = *epi;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPF_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    attr_set = true;
+  }
+  const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
+  const int grid = min(total, num_sms());
+  gemm_bf16_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(ta, tb, g);
+  return check_launch("gemm_bf16_kernel");
+}
