@@ -136,6 +136,94 @@ int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int
                   int M, int N, int K, int splits, const vpf_gemm_epilogue *epi,
                   void *stream);
 
+/* ------------------------------------------------------------------ attention core
+ * MultiHeadAttention.forward between the projections, partseg.py:71-84:
+ * softmax(Q K^T * scale) -> dropout(p) -> . V, per (sample, head); head_dim = 64.
+ * Q/K/V/O are bf16 token-row arrays ([B*L, ld], head h at columns h*64..h*64+63);
+ * LSE fp32 [B*H, Lq] (log2 units) is saved for the backward pass. */
+int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int ldkv,
+                      void *O, int ldo, float *LSE, int B, int H, int Lq, int Lk,
+                      int head_dim, float scale, float drop_p,
+                      const unsigned long long *seed_ptr, unsigned int op_id, void *stream);
+/* delta_ws: fp32 scratch [B*H*Lq]. */
+int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int ldkv,
+                      const void *O, int ldo, const void *dO, int lddo, const float *LSE,
+                      float *delta_ws, void *dQ, int lddq, void *dK, void *dV, int lddkv,
+                      int B, int H, int Lq, int Lk, int head_dim, float scale, float drop_p,
+                      const unsigned long long *seed_ptr, unsigned int op_id, void *stream);
+
+/* ------------------------------------------------------------- normalisation etc.
+ * nn.LayerNorm (partseg.py:101-102,129,194; classifier.py:33), eps as given.
+ * y_bf16 = LN(x + add[row % add_rows]) (optionally ReLU'd); xsum (optional) gets x + add. */
+int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows, float *xsum,
+                      const float *gamma, const float *beta, void *y_bf16, float *mean,
+                      float *rstd, int T, int D, float eps, int relu, void *stream);
+/* dx = dres + LN'(dy) ; dpos[row % pos_rows] += dx ; dgamma/dbeta += ... (all optional but dx). */
+int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const void *y_relu,
+                      const float *mean, const float *rstd, const float *gamma, const float *dres,
+                      void *dx, int dx_bf16, float *dgamma, float *dbeta, float *dpos, int pos_rows,
+                      int T, int D, void *stream);
+/* Residual.dropout backward (partseg.py:201-213): out_bf16 = mask(g)/(1-p); colsum += column sums. */
+int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p,
+                     const unsigned long long *seed_ptr, unsigned int op_id, int T, int N, void *stream);
+/* column sums (+=): sum/sumsq in fp64 (BatchNorm statistics), sum_f32 for bias gradients. */
+int vpf_colsum(const void *x, int x_bf16, double *sum, double *sumsq, float *sum_f32,
+               long long R, int C, void *stream);
+/* nn.BatchNorm1d (utils.py:155,162; partseg.py:520,523): fold batch (training) or running (eval)
+ * statistics into (scale, shift); updates running stats when training.  stats = [sum | sumsq]. */
+int vpf_bn_finalize(const double *stats, long long R, const float *gamma, const float *beta,
+                    float *running_mean, float *running_var, float momentum, float eps, int training,
+                    float *scale, float *shift, float *mean, float *rstd, int C, void *stream);
+int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shift, void *y,
+                 int y_bf16, int relu, long long R, int C, void *stream);
+/* train-mode BN (+ReLU) backward; red = fp64 scratch [2C]; dgamma/dbeta accumulate. */
+int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale,
+               const float *shift, const float *mean, const float *rstd, int relu, double *red,
+               void *dx, int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream);
+int vpf_cast_bf16(const float *x, void *y_bf16, long long n, void *stream);
+int vpf_fill_zero(void *p, long long bytes, void *stream);
+
+/* ------------------------------------------------------------------ pooling, thin ops
+ * max over the S points of a group (utils.py:180,188) with argmax for the backward pass. */
+int vpf_group_max_fwd(const void *x_bf16, void *out_bf16, float *out_f32, uint8_t *argmax,
+                      int G, int S, int C, void *stream);
+int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, void *dx_bf16,
+                      int accumulate, int G, int S, int C, void *stream);
+/* cat(x.max(1)[0], x.mean(1)), partseg.py:547. */
+int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream);
+int vpf_token_pool_bwd(const float *dout, const int *argmax, float *dx, int B, int L, int D, void *stream);
+/* Linear(3, Co) / Conv1d(3, Co, 1) on xyz (classifier.py:32, partseg.py:499, utils.py:154). */
+int vpf_linear3_fwd(const float *p, int ldp, const float *w, const float *b, const float *scale,
+                    const float *shift, void *pre_bf16, void *act_bf16, int act, long long R, int Co,
+                    void *stream);
+int vpf_linear3_stats(const float *p, int ldp, const float *w, const float *b, double *stats,
+                      long long R, int Co, void *stream);
+int vpf_linear3_bwd(const void *dy, int dy_bf16, const float *p, int ldp, float *dW, float *db,
+                    long long R, int Co, void *stream);
+int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float *w, const float *b,
+                       const float *scale, const float *shift, const float *mean, const float *rstd,
+                       double *red, float *dW, float *db, float *dgamma, float *dbeta, long long R,
+                       int Co, void *stream);
+/* Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)', partseg.py:632 (fp32 NHWC -> bf16 rows). */
+int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, void *stream);
+int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream);
+
+/* ------------------------------------------------------------------ loss + optimiser
+ * NT-Xent (lightly 1.1.21 NTXentLoss; call sites pretrain.py:155,196,202). */
+int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *stream);
+int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local,
+                   int col_offset, int half, float temperature, float *lse_out, float *loss_out,
+                   void *stream);
+int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all,
+                   int n_c, int D, int b_local, int col_offset, int half, float temperature,
+                   float gscale, const float *upstream, float *dx, void *stream);
+/* torch.optim.AdamW step (pretrain.py:121-124,210) on a flat buffer, refreshing the bf16 shadow. */
+int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n,
+              const float *lr_ptr, float beta1, float beta2, float eps, float weight_decay,
+              const long long *step_ptr, float grad_scale, void *stream);
+/* state[0] += 1 (optimizer step), state[1] = next dropout seed. */
+int vpf_step_advance(long long *state, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,436 @@
+// attention.cu -- fused multi-head attention core (softmax(Q K^T * scale) V) forward + backward for
+// the small-sequence blocks of partseg.py:67-86: Lq <= 144 query tokens, Lk in {96..144} (self /
+// image) or 1024..2500 (point cross-attention), head dim 64.  Logits never touch HBM.
+//
+// v1 data path: flash-style tiles through shared memory with mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate), online softmax in the exp2 domain, attention-probability dropout (p = atten_drop,
+// partseg.py:81) regenerated from (seed, op_id, element) in the backward pass.  The attention
+// core is ~12 % of the model FLOPs; the 85 % that is Linear/Conv runs on tcgen05 (gemm.cu).
+//
+// Layout: Q rows are token rows of a [B*Lq, ldq] bf16 array, head h at columns [h*64, h*64+64);
+// K/V likewise in [B*Lk, ldkv]; O in [B*Lq, ldo].  LSE is fp32 [B*H, Lq] in log2 units.
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace vpf {
+
+typedef __nv_bfloat16 bf16;
+constexpr int HD = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// A [rows][64] bf16 tile, 128 B per row, 16-byte chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// cooperative load of `rows` x 64 bf16 from global (row stride ld) into a swizzled tile; rows >= valid are zeroed
+__device__ __forceinline__ void load_tile(bf16 *tile, const bf16 *g, int ld, int valid, int rows, int tid, int nthr) {
+  for (int i = tid; i < rows * 8; i += nthr) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < valid) v = *reinterpret_cast<const uint4 *>(g + (size_t)r * ld + c * 8);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(tile) + tile_off(r, c)) = v;
+  }
+}
+
+// A fragments (16 rows x 64 cols) of the tile rows [row0, row0+16): 4 k-steps x 4 regs
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const bf16 *tile, int row0, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    ldsm4(a[kk], smem_addr(tile) + tile_off(row0 + (m & 1) * 8 + r, 2 * kk + (m >> 1)));
+}
+
+// C[16 x 64] += A(16 x 64, frags) * T^T where T is a [64 rows][64] tile: C[i][n] = sum_d A[i][d] T[n][d]
+__device__ __forceinline__ void mma_a_tileT(float (&c)[8][4], const uint32_t (&a)[4][4], const bf16 *tile, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int nb = 0; nb < 8; nb += 2) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b[4];
+      ldsm4(b, smem_addr(tile) + tile_off((nb + (m >> 1)) * 8 + r, 2 * kk + (m & 1)));
+      mma16816(c[nb], a[kk], b[0], b[1]);
+      mma16816(c[nb + 1], a[kk], b[2], b[3]);
+    }
+  }
+}
+
+// C[16 x 64] += P(16 x 64, packed from accumulators) * T where T is a [64 rows][64] tile: C[i][n] = sum_j P[i][j] T[j][n]
+__device__ __forceinline__ void mma_p_tile(float (&c)[8][4], const uint32_t (&p)[4][4], const bf16 *tile, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int nd = 0; nd < 8; nd += 2) {
+      uint32_t b[4];
+      ldsm4t(b, smem_addr(tile) + tile_off(16 * kk + (m & 1) * 8 + r, nd + (m >> 1)));
+      mma16816(c[nd], p[kk], b[0], b[1]);
+      mma16816(c[nd + 1], p[kk], b[2], b[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void pack_p(uint32_t (&p)[4][4], const float (&s)[8][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    p[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    p[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    p[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    p[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  }
+}
+
+struct DropCfg {
+  uint32_t thr, key;
+  float scale;
+};
+__device__ __forceinline__ DropCfg make_drop(float p, const unsigned long long *seed_ptr, uint32_t op_id) {
+  DropCfg d;
+  d.thr = p > 0.f ? rng::threshold(p) : 0u;
+  d.key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
+  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+// element index of attention probability (bh, i, j)
+__device__ __forceinline__ uint32_t prob_index(int bh, int i, int j, int Lq, int Lk) {
+  return ((uint32_t)bh * (uint32_t)Lq + (uint32_t)i) * (uint32_t)Lk + (uint32_t)j;
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V, int ldkv,
+                bf16 *__restrict__ O, int ldo, float *__restrict__ LSE, int H, int Lq, int Lk, float scale,
+                float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
+  __shared__ __align__(128) bf16 sQ[64 * HD];
+  __shared__ __align__(128) bf16 sK[64 * HD];
+  __shared__ __align__(128) bf16 sV[64 * HD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * 64;
+  const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
+
+  load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
+  __syncthreads();
+  uint32_t qa[4][4];
+  load_a_frags(qa, sQ, warp * 16, lane);
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const float sc2 = scale * kLog2e;
+  const int r0 = q0 + warp * 16 + (lane >> 2);  // this thread's first query row (second is +8)
+
+  for (int k0 = 0; k0 < Lk; k0 += 64) {
+    __syncthreads();  // previous tile fully consumed
+    load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+    load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_a_tileT(s, qa, sK, lane);
+    // scale, mask the key tail, running max
+    float mx[2] = {mrow[0], mrow[1]};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+        const float v = j < Lk ? s[nb][e] * sc2 : -INFINITY;
+        s[nb][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], 1));
+      mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], 2));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      corr[t] = exp2f(mrow[t] - mx[t]);  // mrow = -inf on the first tile -> 0
+      mrow[t] = mx[t];
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float p = exp2f(s[nb][e] - mx[e >> 1]);
+        rs[e >> 1] += p;
+        if (dc.thr) {
+          const int i = r0 + (e >> 1) * 8, j = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+          p = rng::keep(dc.key, prob_index(bh, i, j, Lq, Lk), dc.thr) ? p * dc.scale : 0.f;
+        }
+        s[nb][e] = p;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) lrow[t] = lrow[t] * corr[t] + rs[t];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      o[nd][0] *= corr[0]; o[nd][1] *= corr[0];
+      o[nd][2] *= corr[1]; o[nd][3] *= corr[1];
+    }
+    uint32_t pa[4][4];
+    pack_p(pa, s);
+    mma_p_tile(o, pa, sV, lane);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    lrow[t] += __shfl_xor_sync(0xffffffffu, lrow[t], 1);
+    lrow[t] += __shfl_xor_sync(0xffffffffu, lrow[t], 2);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = r0 + t * 8;
+    if (i < Lq) {
+      const float inv = 1.f / lrow[t];
+      bf16 *op = O + ((size_t)b * Lq + i) * ldo + h * HD + (lane & 3) * 2;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        *reinterpret_cast<uint32_t *>(op + nd * 8) = pack_bf16(o[nd][2 * t] * inv, o[nd][2 * t + 1] * inv);
+      if ((lane & 3) == 0) LSE[(size_t)bh * Lq + i] = mrow[t] + log2f(lrow[t]);
+    }
+  }
+}
+
+// delta[bh, i] = sum_d dO[i, d] * O[i, d]
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16 *__restrict__ O, int ldo, const bf16 *__restrict__ dO, int lddo, float *__restrict__ delta,
+                  int H, int Lq, long long total) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;  // over (b, i, h)
+  if (t >= total) return;
+  const int h = (int)(t % H);
+  const long long row = t / H;  // b*Lq + i
+  const int b = (int)(row / Lq), i = (int)(row % Lq);
+  const uint4 *po = reinterpret_cast<const uint4 *>(O + (size_t)row * ldo + h * HD);
+  const uint4 *pd = reinterpret_cast<const uint4 *>(dO + (size_t)row * lddo + h * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 a = po[c], d = pd[c];
+    const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 fa = __bfloat1622float2(ha[q]), fd = __bfloat1622float2(hd[q]);
+      acc += fa.x * fd.x + fa.y * fd.y;
+    }
+  }
+  delta[((size_t)b * H + h) * Lq + i] = acc;
+}
+
+// ------------------------------------------------- backward: dK, dV (per key block)
+// Each warp owns 16 keys and walks all queries in chunks of 64, working on S^T = K Q^T.
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
+                    int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
+                    const float *__restrict__ delta, bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H,
+                    int Lq, int Lk, float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr,
+                    uint32_t op_id) {
+  __shared__ __align__(128) bf16 sK[64 * HD];
+  __shared__ __align__(128) bf16 sV[64 * HD];
+  __shared__ __align__(128) bf16 sQ[64 * HD];
+  __shared__ __align__(128) bf16 sdO[64 * HD];
+  __shared__ float sLse[64], sDelta[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.x * 64;
+  const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
+  const float sc2 = scale * kLog2e;
+
+  load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+  load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+  __syncthreads();
+  uint32_t ka[4][4], va[4][4];
+  load_a_frags(ka, sK, warp * 16, lane);
+  load_a_frags(va, sV, warp * 16, lane);
+
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  const int jrow = k0 + warp * 16 + (lane >> 2);  // this thread's first key (second is +8)
+
+  for (int q0 = 0; q0 < Lq; q0 += 64) {
+    __syncthreads();
+    load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
+    load_tile(sdO, dO + ((size_t)b * Lq + q0) * lddo + h * HD, lddo, Lq - q0, 64, tid, 128);
+    if (tid < 64) {
+      const int i = q0 + tid;
+      sLse[tid] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;   // +inf -> p = 0 for padded queries
+      sDelta[tid] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    mma_a_tileT(st, ka, sQ, lane);    // S^T[key][q]
+    mma_a_tileT(dp, va, sdO, lane);   // dP^T[key][q] = V dO^T
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ql = nb * 8 + (lane & 3) * 2 + (e & 1);
+        const int j = jrow + (e >> 1) * 8;
+        float p = j < Lk ? exp2f(st[nb][e] * sc2 - sLse[ql]) : 0.f;
+        float dpe = dp[nb][e];
+        float pd = p;
+        if (dc.thr) {
+          const bool keep = rng::keep(dc.key, prob_index(bh, q0 + ql, j, Lq, Lk), dc.thr);
+          pd = keep ? p * dc.scale : 0.f;
+          dpe = keep ? dpe * dc.scale : 0.f;
+        }
+        st[nb][e] = pd;                                   // dropped P^T (for dV)
+        dp[nb][e] = p * (dpe - sDelta[ql]) * scale;       // dS^T (for dK)
+      }
+    }
+    uint32_t pa[4][4];
+    pack_p(pa, st);
+    mma_p_tile(dv, pa, sdO, lane);   // dV += P^T dO
+    pack_p(pa, dp);
+    mma_p_tile(dk, pa, sQ, lane);    // dK += dS^T Q
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int j = jrow + t * 8;
+    if (j < Lk) {
+      bf16 *pk = dK + ((size_t)b * Lk + j) * lddkv + h * HD + (lane & 3) * 2;
+      bf16 *pv = dV + ((size_t)b * Lk + j) * lddkv + h * HD + (lane & 3) * 2;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        *reinterpret_cast<uint32_t *>(pk + nd * 8) = pack_bf16(dk[nd][2 * t], dk[nd][2 * t + 1]);
+        *reinterpret_cast<uint32_t *>(pv + nd * 8) = pack_bf16(dv[nd][2 * t], dv[nd][2 * t + 1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------ backward: dQ (per query block)
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
+                   int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
+                   const float *__restrict__ delta, bf16 *__restrict__ dQ, int lddq, int H, int Lq, int Lk,
+                   float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
+  __shared__ __align__(128) bf16 sQ[64 * HD];
+  __shared__ __align__(128) bf16 sdO[64 * HD];
+  __shared__ __align__(128) bf16 sK[64 * HD];
+  __shared__ __align__(128) bf16 sV[64 * HD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * 64;
+  const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
+  const float sc2 = scale * kLog2e;
+
+  load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
+  load_tile(sdO, dO + ((size_t)b * Lq + q0) * lddo + h * HD, lddo, Lq - q0, 64, tid, 128);
+  __syncthreads();
+  uint32_t qa[4][4], da[4][4];
+  load_a_frags(qa, sQ, warp * 16, lane);
+  load_a_frags(da, sdO, warp * 16, lane);
+  const int r0 = q0 + warp * 16 + (lane >> 2);
+  float lse[2], dl[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = r0 + t * 8;
+    lse[t] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
+    dl[t] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+  }
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+  for (int k0 = 0; k0 < Lk; k0 += 64) {
+    __syncthreads();
+    load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+    load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    mma_a_tileT(s, qa, sK, lane);    // S = Q K^T
+    mma_a_tileT(dp, da, sV, lane);   // dP = dO V^T
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+        const float p = j < Lk ? exp2f(s[nb][e] * sc2 - lse[e >> 1]) : 0.f;
+        float dpe = dp[nb][e];
+        if (dc.thr) dpe = rng::keep(dc.key, prob_index(bh, r0 + (e >> 1) * 8, j, Lq, Lk), dc.thr) ? dpe * dc.scale : 0.f;
+        s[nb][e] = p * (dpe - dl[e >> 1]) * scale;  // dS
+      }
+    }
+    uint32_t pa[4][4];
+    pack_p(pa, s);
+    mma_p_tile(dq, pa, sK, lane);    // dQ += dS K
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = r0 + t * 8;
+    if (i < Lq) {
+      bf16 *pq = dQ + ((size_t)b * Lq + i) * lddq + h * HD + (lane & 3) * 2;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t *>(pq + nd * 8) = pack_bf16(dq[nd][2 * t], dq[nd][2 * t + 1]);
+    }
+  }
+}
+
+}  // namespace vpf
+
+using namespace vpf;
+
+extern "C" {
+
+int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, void *O, int ldo, float *LSE,
+                      int B, int H, int Lq, int Lk, int head_dim, float scale, float drop_p,
+                      const unsigned long long *seed_ptr, unsigned int op_id, void *stream) {
+  VPF_REQUIRE(Q && K && V && O && LSE, "attention_fwd: null pointer");
+  VPF_REQUIRE(head_dim == HD, "attention_fwd: head_dim=%d unsupported (64)", head_dim);
+  VPF_REQUIRE(Lq >= 1 && Lk >= 1 && H >= 1 && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0, "attention_fwd: bad shape/stride");
+  VPF_REQUIRE((long long)B * H <= 65535 * 1LL * 65535, "attention_fwd: too many heads");
+  if (B == 0) return VPF_OK;
+  attn_fwd_kernel<<<dim3(ceil_div(Lq, 64), B * H), 128, 0, (cudaStream_t)stream>>>(
+      (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (bf16 *)O, ldo, LSE, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  return check_launch("attn_fwd_kernel");
+}
+
+int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, const void *O, int ldo,
+                      const void *dO, int lddo, const float *LSE, float *delta_ws, void *dQ, int lddq, void *dK,
+                      void *dV, int lddkv, int B, int H, int Lq, int Lk, int head_dim, float scale, float drop_p,
+                      const unsigned long long *seed_ptr, unsigned int op_id, void *stream) {
+  VPF_REQUIRE(Q && K && V && O && dO && LSE && delta_ws && dQ && dK && dV, "attention_bwd: null pointer");
+  VPF_REQUIRE(head_dim == HD, "attention_bwd: head_dim=%d unsupported (64)", head_dim);
+  VPF_REQUIRE((ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddkv % 2) == 0, "attention_bwd: bad stride");
+  if (B == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * Lq * H;
+  attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
+  VPF_TRY(check_launch("attn_delta_kernel"));
+  attn_bwd_dkv_kernel<<<dim3(ceil_div(Lk, 64), B * H), 128, 0, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
+                                                                      (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  VPF_TRY(check_launch("attn_bwd_dkv_kernel"));
+  attn_bwd_dq_kernel<<<dim3(ceil_div(Lq, 64), B * H), 128, 0, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
+                                                                     (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  return check_launch("attn_bwd_dq_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,413 @@
+// norm.cu -- LayerNorm / BatchNorm / dropout-gradient / column-reduction kernels (fp32 math,
+// bf16 or fp32 storage).  Reference semantics:
+//   nn.LayerNorm (eps 1e-5, biased variance)       partseg.py:101-102,129,194  classifier.py:33
+//   nn.BatchNorm1d train mode (eps 1e-5, momentum 0.1, biased var to normalise, unbiased var
+//   into running_var)                              utils.py:155,162  partseg.py:520,523
+//   nn.Dropout inside Residual                     partseg.py:201-213
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace vpf {
+
+template <typename T> __device__ __forceinline__ float ldf(const T *p, size_t i);
+template <> __device__ __forceinline__ float ldf<float>(const float *p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16 *p, size_t i) { return __bfloat162float(p[i]); }
+template <typename T> __device__ __forceinline__ void stf(T *p, size_t i, float v);
+template <> __device__ __forceinline__ void stf<float>(float *p, size_t i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16 *p, size_t i, float v) { p[i] = __float2bfloat16(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------- LayerNorm fwd
+// one warp per row; NPER = D/32 values per lane held in registers
+template <typename Tin, int NPER>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
+              const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
+              float *__restrict__ mean_out, float *__restrict__ rstd_out, int T, float eps, int relu) {
+  constexpr int D = NPER * 32;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  float v[NPER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int c = lane + 32 * i;
+    float t = ldf<Tin>(x, (size_t)row * D + c);
+    if (add) t += add[(size_t)(row % add_rows) * D + c];
+    v[i] = t;
+    s += t;
+  }
+  if (xsum) {
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) xsum[(size_t)row * D + lane + 32 * i] = v[i];
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int c = lane + 32 * i;
+    float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (relu) o = fmaxf(o, 0.f);
+    y[(size_t)row * D + c] = __float2bfloat16(o);
+  }
+}
+
+// ------------------------------------------------------------- LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = gamma * dy  (dy masked by y > 0 when relu)
+// dx_out = dres + dx;  dpos[row % pos_rows] += dx_out;  dgamma += sum dy*xhat;  dbeta += sum dy
+template <typename Tdy, typename Tx, typename Tdx, int NPER>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_bfloat16 *__restrict__ y_relu,
+              const float *__restrict__ mean_in, const float *__restrict__ rstd_in, const float *__restrict__ gamma,
+              const float *__restrict__ dres, Tdx *__restrict__ dx, float *__restrict__ dgamma,
+              float *__restrict__ dbeta, float *__restrict__ dpos, int pos_rows, int T, int rows_per_cta) {
+  constexpr int D = NPER * 32;
+  __shared__ float s_dg[D], s_db[D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dg[NPER], db[NPER];
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) dg[i] = db[i] = 0.f;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(T, row0 + rows_per_cta);
+  for (int row = row0 + warp; row < row1; row += 8) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g[NPER], xh[NPER];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float d = ldf<Tdy>(dy, (size_t)row * D + c);
+      if (y_relu && !(__bfloat162float(y_relu[(size_t)row * D + c]) > 0.f)) d = 0.f;
+      xh[i] = (ldf<Tx>(x, (size_t)row * D + c) - mean) * rstd;
+      dg[i] += d * xh[i];
+      db[i] += d;
+      g[i] = d * gamma[c];
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float o = rstd * (g[i] - s1 - xh[i] * s2);
+      if (dres) o += dres[(size_t)row * D + c];
+      stf<Tdx>(dx, (size_t)row * D + c, o);
+      if (dpos) {
+        if (pos_rows >= T) dpos[(size_t)row * D + c] += o;
+        else atomicAdd(dpos + (size_t)(row % pos_rows) * D + c, o);
+      }
+    }
+  }
+  if (dgamma) {
+    for (int c = threadIdx.x; c < D; c += 256) { s_dg[c] = 0.f; s_db[c] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) { atomicAdd(&s_dg[lane + 32 * i], dg[i]); atomicAdd(&s_db[lane + 32 * i], db[i]); }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      atomicAdd(dgamma + c, s_dg[c]);
+      atomicAdd(dbeta + c, s_db[c]);
+    }
+  }
+}
+
+// --------------------------------------------- residual-branch gradient prep
+// out_bf16 = dropout_mask(g) (same (seed, op_id, index) stream as the forward epilogue); colsum += sum_rows(out)
+__global__ void __launch_bounds__(256)
+dropout_grad_kernel(const float *__restrict__ g, __nv_bfloat16 *__restrict__ out, float *__restrict__ colsum,
+                    float p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id, int T, int N,
+                    int rows_per_cta) {
+  const uint32_t thr = p > 0.f ? rng::threshold(p) : 0u;
+  const uint32_t key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int row0 = blockIdx.x * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float acc = 0.f;
+    for (int r = row0; r < row1; ++r) {
+      const size_t e = (size_t)r * N + c;
+      float v = g[e];
+      if (thr) v = rng::keep(key, (uint32_t)e, thr) ? v * scale : 0.f;
+      out[e] = __float2bfloat16(v);
+      acc += v;
+    }
+    if (colsum) atomicAdd(colsum + c, acc);
+  }
+}
+
+// ------------------------------------------------------ column sum / sumsq
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T *__restrict__ x, double *__restrict__ sum, double *__restrict__ sumsq, float *__restrict__ sum_f32,
+              long long R, int C, int rows_per_cta) {
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (int c = threadIdx.x + blockIdx.y * 256; c < C; c += 256 * gridDim.y) {
+    double a = 0.0, q = 0.0;
+    for (long long r0 = row0; r0 < row1; r0 += 64) {
+      float pa = 0.f, pq = 0.f;
+      const long long r1 = min(row1, r0 + 64);
+      for (long long r = r0; r < r1; ++r) { const float v = ldf<T>(x, (size_t)r * C + c); pa += v; pq += v * v; }
+      a += pa; q += pq;
+    }
+    if (sum) atomicAdd(sum + c, a);
+    if (sumsq) atomicAdd(sumsq + c, q);
+    if (sum_f32) atomicAdd(sum_f32 + c, (float)a);
+  }
+}
+
+// ------------------------------------------------------------- BatchNorm1d
+// stats[0..C) = sum, stats[C..2C) = sumsq (double).  Writes the folded affine (scale, shift) and (mean, rstd).
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, long long R, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float *__restrict__ running_mean,
+                                   float *__restrict__ running_var, float momentum, float eps, int training,
+                                   float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
+                                   float *__restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = stats[c] / (double)R;
+    double v = stats[C + c] / (double)R - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      const double unb = R > 1 ? v * (double)R / (double)(R - 1) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const Tin *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
+                Tout *__restrict__ y, int relu, size_t total, int C) {
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int c = (int)(e % C);
+    float v = ldf<Tin>(x, e) * scale[c] + shift[c];
+    if (relu) v = fmaxf(v, 0.f);
+    stf<Tout>(y, e, v);
+  }
+}
+
+// phase 1 of BN backward: red[0..C) += sum dyb, red[C..2C) += sum dyb * xhat   (dyb = relu-masked dy)
+template <typename Tdy, typename Tx>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const float *__restrict__ scale,
+                     const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                     int relu, double *__restrict__ red, long long R, int C, int rows_per_cta) {
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (int c = threadIdx.x + blockIdx.y * 256; c < C; c += 256 * gridDim.y) {
+    const float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
+    double a = 0.0, q = 0.0;
+    for (long long r0 = row0; r0 < row1; r0 += 64) {
+      float pa = 0.f, pq = 0.f;
+      const long long r1 = min(row1, r0 + 64);
+      for (long long r = r0; r < r1; ++r) {
+        const float xv = ldf<Tx>(x, (size_t)r * C + c);
+        float d = ldf<Tdy>(dy, (size_t)r * C + c);
+        if (relu && !(xv * sc + sh > 0.f)) d = 0.f;
+        pa += d;
+        pq += d * (xv - mu) * rs;
+      }
+      a += pa; q += pq;
+    }
+    atomicAdd(red + c, a);
+    atomicAdd(red + C + c, q);
+  }
+}
+
+// phase 2: dx = gamma*rstd * (dyb - sum_dyb/R - xhat * sum_dyb_xhat/R); CTA 0 also emits dgamma/dbeta (+=)
+template <typename Tdy, typename Tx, typename Tdx>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const float *__restrict__ scale,
+                    const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                    int relu, const double *__restrict__ red, Tdx *__restrict__ dx, float *__restrict__ dgamma,
+                    float *__restrict__ dbeta, long long R, int C) {
+  const size_t total = (size_t)R * C;
+  const double invR = 1.0 / (double)R;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int c = (int)(e % C);
+    const float sc = scale[c], sh = shift[c];
+    const float xv = ldf<Tx>(x, e);
+    float d = ldf<Tdy>(dy, e);
+    if (relu && !(xv * sc + sh > 0.f)) d = 0.f;
+    const float xh = (xv - mean[c]) * rstd[c];
+    const float m1 = (float)(red[c] * invR), m2 = (float)(red[C + c] * invR);
+    stf<Tdx>(dx, e, sc * (d - m1 - xh * m2));
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      dgamma[c] += (float)red[C + c];
+      dbeta[c] += (float)red[c];
+    }
+  }
+}
+
+__global__ void cast_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) y[i] = __float2bfloat16(x[i]);
+}
+
+static inline int grid_for(size_t total) { return (int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)); }
+
+}  // namespace vpf
+
+using namespace vpf;
+typedef __nv_bfloat16 bf16;
+
+#define LN_DISPATCH(D, MACRO)                                                                       \
+  switch (D) {                                                                                      \
+    case 64: MACRO(2); break; case 128: MACRO(4); break; case 256: MACRO(8); break;                 \
+    case 384: MACRO(12); break; case 512: MACRO(16); break; case 768: MACRO(24); break;             \
+    case 1024: MACRO(32); break;                                                                    \
+    default: return fail(VPF_EINVAL, "layernorm: D=%d unsupported (64,128,256,384,512,768,1024)", D); \
+  }
+
+extern "C" {
+
+int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows, float *xsum, const float *gamma,
+                      const float *beta, void *y_bf16, float *mean, float *rstd, int T, int D, float eps, int relu,
+                      void *stream) {
+  VPF_REQUIRE(x && gamma && beta && y_bf16, "layernorm_fwd: null pointer");
+  VPF_REQUIRE(!add || add_rows > 0, "layernorm_fwd: add_rows must be > 0");
+  if (T == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(T, 8);
+#define LNF(NP)                                                                                                     \
+  if (x_bf16) ln_fwd_kernel<bf16, NP><<<grid, 256, 0, st>>>((const bf16 *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
+  else ln_fwd_kernel<float, NP><<<grid, 256, 0, st>>>((const float *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu)
+  LN_DISPATCH(D, LNF)
+#undef LNF
+  return check_launch("ln_fwd_kernel");
+}
+
+int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const void *y_relu, const float *mean,
+                      const float *rstd, const float *gamma, const float *dres, void *dx, int dx_bf16, float *dgamma,
+                      float *dbeta, float *dpos, int pos_rows, int T, int D, void *stream) {
+  VPF_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
+  VPF_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be given or both null");
+  if (T == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows_per_cta = max(8, ceil_div(T, num_sms() * 4));
+  const int grid = ceil_div(T, rows_per_cta);
+#define LNB_CALL(TDY, TX, TDX, NP)                                                                                    \
+  ln_bwd_kernel<TDY, TX, TDX, NP><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
+                                                         (TDX *)dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta)
+#define LNB(NP)                                                                     \
+  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP);                 \
+  else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP);          \
+  else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP);      \
+  else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP);        \
+  else if (dy_bf16 && x_bf16 && !dx_bf16) LNB_CALL(bf16, bf16, float, NP);          \
+  else return fail(VPF_EINVAL, "layernorm_bwd: unsupported dtype combination dy_bf16=%d x_bf16=%d dx_bf16=%d", dy_bf16, x_bf16, dx_bf16)
+  LN_DISPATCH(D, LNB)
+#undef LNB
+#undef LNB_CALL
+  return check_launch("ln_bwd_kernel");
+}
+
+int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p, const unsigned long long *seed_ptr,
+                     unsigned int op_id, int T, int N, void *stream) {
+  VPF_REQUIRE(g && out_bf16, "dropout_grad: null pointer");
+  VPF_REQUIRE(p >= 0.f && p < 1.f, "dropout_grad: p=%f out of range", p);
+  VPF_REQUIRE((size_t)T * (size_t)N < (1ull << 32), "dropout_grad: index space exceeds 2^32");
+  if (T == 0 || N == 0) return VPF_OK;
+  const int rows_per_cta = max(1, ceil_div(T, num_sms() * 8));
+  dropout_grad_kernel<<<ceil_div(T, rows_per_cta), 256, 0, (cudaStream_t)stream>>>(g, (bf16 *)out_bf16, colsum, p, seed_ptr, op_id, T, N, rows_per_cta);
+  return check_launch("dropout_grad_kernel");
+}
+
+int vpf_colsum(const void *x, int x_bf16, double *sum, double *sumsq, float *sum_f32, long long R, int C, void *stream) {
+  VPF_REQUIRE(x && (sum || sumsq || sum_f32), "colsum: null pointer");
+  if (R == 0 || C == 0) return VPF_OK;
+  const int gy = ceil_div(C, 256);
+  const int rows_per_cta = (int)max((long long)64, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
+  dim3 grid((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
+  if (x_bf16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, sum, sumsq, sum_f32, R, C, rows_per_cta);
+  else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)x, sum, sumsq, sum_f32, R, C, rows_per_cta);
+  return check_launch("colsum_kernel");
+}
+
+int vpf_bn_finalize(const double *stats, long long R, const float *gamma, const float *beta, float *running_mean,
+                    float *running_var, float momentum, float eps, int training, float *scale, float *shift,
+                    float *mean, float *rstd, int C, void *stream) {
+  VPF_REQUIRE(gamma && beta && scale && shift && mean && rstd, "bn_finalize: null pointer");
+  VPF_REQUIRE(training ? (stats != nullptr && R > 0) : (running_mean && running_var), "bn_finalize: missing statistics");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, R, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift, mean, rstd, C);
+  return check_launch("bn_finalize_kernel");
+}
+
+int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shift, void *y, int y_bf16, int relu,
+                 long long R, int C, void *stream) {
+  VPF_REQUIRE(x && scale && shift && y, "bn_apply: null pointer");
+  const size_t total = (size_t)R * C;
+  if (total == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(total);
+  if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
+  else if (!x_bf16 && y_bf16) bn_apply_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (bf16 *)y, relu, total, C);
+  else if (!x_bf16 && !y_bf16) bn_apply_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (float *)y, relu, total, C);
+  else return fail(VPF_EINVAL, "bn_apply: bf16 -> fp32 unsupported");
+  return check_launch("bn_apply_kernel");
+}
+
+int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale, const float *shift,
+               const float *mean, const float *rstd, int relu, double *red /*[2C], zeroed by the callee*/, void *dx,
+               int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream) {
+  VPF_REQUIRE(dy && x && scale && shift && mean && rstd && red && dx, "bn_bwd: null pointer");
+  if (R == 0 || C == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VPF_CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
+  const int gy = ceil_div(C, 256);
+  const int rows_per_cta = (int)max((long long)64, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
+  dim3 grid((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
+  const int g2 = grid_for((size_t)R * C);
+#define BNB(TDY, TX, TDX)                                                                                                   \
+  {                                                                                                                         \
+    bn_bwd_reduce_kernel<TDY, TX><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, R, C, rows_per_cta); \
+    VPF_TRY(check_launch("bn_bwd_reduce_kernel"));                                                                          \
+    bn_bwd_apply_kernel<TDY, TX, TDX><<<g2, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, (TDX *)dx, dgamma, dbeta, R, C); \
+  }
+  if (dy_bf16 && x_bf16 && dx_bf16) BNB(bf16, bf16, bf16)
+  else if (!dy_bf16 && !x_bf16 && !dx_bf16) BNB(float, float, float)
+  else if (dy_bf16 && !x_bf16 && dx_bf16) BNB(bf16, float, bf16)
+  else if (!dy_bf16 && x_bf16 && dx_bf16) BNB(float, bf16, bf16)
+  else return fail(VPF_EINVAL, "bn_bwd: unsupported dtype combination");
+#undef BNB
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+int vpf_cast_bf16(const float *x, void *y_bf16, long long n, void *stream) {
+  VPF_REQUIRE(x && y_bf16, "cast_bf16: null pointer");
+  if (n == 0) return VPF_OK;
+  cast_bf16_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, (bf16 *)y_bf16, (size_t)n);
+  return check_launch("cast_bf16_kernel");
+}
+
+int vpf_fill_zero(void *p, long long bytes, void *stream) {
+  VPF_REQUIRE(p || bytes == 0, "fill_zero: null pointer");
+  if (bytes == 0) return VPF_OK;
+  VPF_CUDA_TRY(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+  return VPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,313 @@
+// pool.cu -- max/mean pooling, K=3 linears (too thin for tensor cores), image patchify.
+// Reference semantics:
+//   torch.max over the 32 neighbours of a group      utils.py:180,188   (first max wins)
+//   cat(x.max(1)[0], x.mean(1))                      partseg.py:547
+//   nn.Linear(3, 64|128) / Conv1d(3, 64, 1)          classifier.py:32  partseg.py:499  utils.py:154
+//   Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)'   partseg.py:632
+#include "common.cuh"
+
+namespace vpf {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ---------------------------------------------------------------- group max
+// x bf16 [G,S,C] -> max over S (first index wins); out_bf16 / out_f32 optional; argmax u8 [G,C]
+__global__ void __launch_bounds__(128)
+group_max_fwd_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ out_bf16, float *__restrict__ out_f32,
+                     uint8_t *__restrict__ argmax, int S, int C) {
+  const int g = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const bf16 *p = x + (size_t)g * S * C + c;
+  float best = __bfloat162float(p[0]);
+  int bi = 0;
+  for (int s = 1; s < S; ++s) {
+    const float v = __bfloat162float(p[(size_t)s * C]);
+    if (v > best) { best = v; bi = s; }
+  }
+  const size_t o = (size_t)g * C + c;
+  if (out_bf16) out_bf16[o] = __float2bfloat16(best);
+  if (out_f32) out_f32[o] = best;
+  argmax[o] = (uint8_t)bi;
+}
+
+// dx[g,s,c] (+)= (s == argmax[g,c]) ? dout[g,c] : 0
+template <typename Tdo>
+__global__ void __launch_bounds__(128)
+group_max_bwd_kernel(const Tdo *__restrict__ dout, const uint8_t *__restrict__ argmax, bf16 *__restrict__ dx,
+                     int accumulate, int S, int C) {
+  const int g = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const size_t o = (size_t)g * C + c;
+  const int am = argmax[o];
+  float d;
+  if constexpr (sizeof(Tdo) == 4) d = dout[o]; else d = __bfloat162float(dout[o]);
+  bf16 *p = dx + (size_t)g * S * C + c;
+  if (accumulate) {
+    p[(size_t)am * C] = __float2bfloat16(__bfloat162float(p[(size_t)am * C]) + d);
+  } else {
+    const bf16 z = __float2bfloat16(0.f), dv = __float2bfloat16(d);
+    for (int s = 0; s < S; ++s) p[(size_t)s * C] = (s == am) ? dv : z;
+  }
+}
+
+// --------------------------------------------------------------- token pool
+// x fp32 [B,L,D] -> out fp32 [B,2D] = (max_l || mean_l); argmax int32 [B,D]
+__global__ void __launch_bounds__(128)
+token_pool_fwd_kernel(const float *__restrict__ x, float *__restrict__ out, int *__restrict__ argmax, int L, int D) {
+  const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= D) return;
+  const float *p = x + (size_t)b * L * D + c;
+  float best = p[0], sum = p[0];
+  int bi = 0;
+  for (int l = 1; l < L; ++l) {
+    const float v = p[(size_t)l * D];
+    sum += v;
+    if (v > best) { best = v; bi = l; }
+  }
+  out[(size_t)b * 2 * D + c] = best;
+  out[(size_t)b * 2 * D + D + c] = sum / (float)L;
+  argmax[(size_t)b * D + c] = bi;
+}
+__global__ void __launch_bounds__(128)
+token_pool_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ argmax, float *__restrict__ dx, int L, int D) {
+  const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= D) return;
+  const float dmax = dout[(size_t)b * 2 * D + c], dmean = dout[(size_t)b * 2 * D + D + c] / (float)L;
+  const int am = argmax[(size_t)b * D + c];
+  float *p = dx + (size_t)b * L * D + c;
+  for (int l = 0; l < L; ++l) p[(size_t)l * D] = dmean + (l == am ? dmax : 0.f);
+}
+
+// ------------------------------------------------------------ K = 3 linears
+// y = ((w.p + b) * scale + shift) ; pre (optional, bf16) gets y; act (optional, bf16) gets act(y)
+__global__ void __launch_bounds__(256)
+linear3_fwd_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
+                   const float *__restrict__ scale, const float *__restrict__ shift, bf16 *__restrict__ pre,
+                   bf16 *__restrict__ actout, int act, long long R, int Co) {
+  const size_t total = (size_t)R * Co;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int c = (int)(e % Co);
+    const size_t r = e / Co;
+    const float *q = p + r * ldp;
+    float y = fmaf(w[c * 3 + 2], q[2], fmaf(w[c * 3 + 1], q[1], w[c * 3] * q[0])) + b[c];
+    if (scale) y = y * scale[c] + shift[c];
+    if (pre) pre[e] = __float2bfloat16(y);
+    if (actout) {
+      if (act == VPF_ACT_RELU) y = fmaxf(y, 0.f);
+      else if (act == VPF_ACT_GELU) y = gelu_exact(y);
+      actout[e] = __float2bfloat16(y);
+    }
+  }
+}
+
+// column statistics of y = w.p + b without materialising it: stats[0..Co) += sum, stats[Co..2Co) += sumsq
+__global__ void __launch_bounds__(256)
+linear3_stats_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
+                     double *__restrict__ stats, long long R, int Co, int rows_per_cta) {
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (int c = threadIdx.x; c < Co; c += 256) {
+    const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = b[c];
+    double a = 0.0, q = 0.0;
+    for (long long r0 = row0; r0 < row1; r0 += 64) {
+      float pa = 0.f, pq = 0.f;
+      const long long r1 = min(row1, r0 + 64);
+      for (long long r = r0; r < r1; ++r) {
+        const float *x = p + (size_t)r * ldp;
+        const float y = fmaf(w2, x[2], fmaf(w1, x[1], w0 * x[0])) + bb;
+        pa += y; pq += y * y;
+      }
+      a += pa; q += pq;
+    }
+    atomicAdd(stats + c, a);
+    atomicAdd(stats + Co + c, q);
+  }
+}
+
+// dW[c][j] += sum_r dy[r,c] p[r,j];  db[c] += sum_r dy[r,c]
+template <typename Tdy>
+__global__ void __launch_bounds__(256)
+linear3_bwd_kernel(const Tdy *__restrict__ dy, const float *__restrict__ p, int ldp, float *__restrict__ dW,
+                   float *__restrict__ db, long long R, int Co, int rows_per_cta) {
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (int c = threadIdx.x; c < Co; c += 256) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+    for (long long r = row0; r < row1; ++r) {
+      float d;
+      if constexpr (sizeof(Tdy) == 4) d = dy[(size_t)r * Co + c]; else d = __bfloat162float(dy[(size_t)r * Co + c]);
+      const float *x = p + (size_t)r * ldp;
+      a0 += d * x[0]; a1 += d * x[1]; a2 += d * x[2]; ab += d;
+    }
+    atomicAdd(dW + c * 3 + 0, a0); atomicAdd(dW + c * 3 + 1, a1); atomicAdd(dW + c * 3 + 2, a2);
+    atomicAdd(db + c, ab);
+  }
+}
+
+// BN(train)+ReLU backward through y = w.p + b recomputed on the fly (Group2Emb first_conv.0-2, utils.py:154-156).
+// phase 1: red[0..Co) += sum dyb, red[Co..2Co) += sum dyb*xhat
+// phase 2: dy1 = scale*(dyb - m1 - xhat*m2): dW += dy1^T p, db += sum dy1   (dy1 never stored)
+template <int PHASE>
+__global__ void __launch_bounds__(256)
+linear3_bn_bwd_kernel(const bf16 *__restrict__ dh, const float *__restrict__ p, int ldp, const float *__restrict__ w,
+                      const float *__restrict__ b, const float *__restrict__ scale, const float *__restrict__ shift,
+                      const float *__restrict__ mean, const float *__restrict__ rstd, double *__restrict__ red,
+                      float *__restrict__ dW, float *__restrict__ db, long long R, int Co, int rows_per_cta) {
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (int c = threadIdx.x; c < Co; c += 256) {
+    const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = b[c];
+    const float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
+    float m1 = 0.f, m2 = 0.f;
+    if (PHASE == 2) { m1 = (float)(red[c] / (double)R); m2 = (float)(red[Co + c] / (double)R); }
+    double a = 0.0, q = 0.0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+    for (long long r0 = row0; r0 < row1; r0 += 64) {
+      float pa = 0.f, pq = 0.f;
+      const long long r1 = min(row1, r0 + 64);
+      for (long long r = r0; r < r1; ++r) {
+        const float *x = p + (size_t)r * ldp;
+        const float y = fmaf(w2, x[2], fmaf(w1, x[1], w0 * x[0])) + bb;
+        float d = __bfloat162float(dh[(size_t)r * Co + c]);
+        if (!(y * sc + sh > 0.f)) d = 0.f;
+        const float xh = (y - mu) * rs;
+        if (PHASE == 1) { pa += d; pq += d * xh; }
+        else {
+          const float g = sc * (d - m1 - xh * m2);
+          a0 += g * x[0]; a1 += g * x[1]; a2 += g * x[2]; ab += g;
+        }
+      }
+      a += pa; q += pq;
+    }
+    if (PHASE == 1) { atomicAdd(red + c, a); atomicAdd(red + Co + c, q); }
+    else {
+      atomicAdd(dW + c * 3 + 0, a0); atomicAdd(dW + c * 3 + 1, a1); atomicAdd(dW + c * 3 + 2, a2);
+      atomicAdd(db + c, ab);
+    }
+  }
+}
+__global__ void bn_param_grad_kernel(const double *__restrict__ red, float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
+}
+
+// ----------------------------------------------------------------- patchify
+// img fp32 [B,H,W,Ci] -> out bf16 [B*(H/P)*(W/P), P*P*Ci] in (p1 p2 c) order
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float *__restrict__ img, bf16 *__restrict__ out, int H, int W, int Ci, int P, size_t total) {
+  const int nw = W / P, nh = H / P, pd = P * P * Ci;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int k = (int)(e % pd);
+    const size_t row = e / pd;
+    const int pw = (int)(row % nw), ph = (int)((row / nw) % nh);
+    const size_t b = row / ((size_t)nw * nh);
+    const int c = k % Ci, p2 = (k / Ci) % P, p1 = k / (Ci * P);
+    out[e] = __float2bfloat16(img[((b * H + (size_t)ph * P + p1) * W + (size_t)pw * P + p2) * Ci + c]);
+  }
+}
+
+// out = alpha * (a + b)   /   batch-sum reduce: out[r % rows] += x[r]
+__global__ void add_scale_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, float alpha, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = alpha * (a[i] + (b ? b[i] : 0.f));
+}
+
+static inline int grid_for(size_t total) { return (int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)); }
+static inline int rows_per_cta_for(long long R) { return (int)max((long long)64, ceil_div(R, (long long)num_sms() * 8)); }
+
+}  // namespace vpf
+
+using namespace vpf;
+
+extern "C" {
+
+int vpf_group_max_fwd(const void *x_bf16, void *out_bf16, float *out_f32, uint8_t *argmax, int G, int S, int C, void *stream) {
+  VPF_REQUIRE(x_bf16 && argmax && (out_bf16 || out_f32), "group_max_fwd: null pointer");
+  VPF_REQUIRE(S >= 1 && S <= 255, "group_max_fwd: S=%d unsupported", S);
+  if (G == 0 || C == 0) return VPF_OK;
+  group_max_fwd_kernel<<<dim3(G, ceil_div(C, 128)), 128, 0, (cudaStream_t)stream>>>((const bf16 *)x_bf16, (bf16 *)out_bf16, out_f32, argmax, S, C);
+  return check_launch("group_max_fwd_kernel");
+}
+
+int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, void *dx_bf16, int accumulate, int G, int S, int C, void *stream) {
+  VPF_REQUIRE(dout && argmax && dx_bf16, "group_max_bwd: null pointer");
+  if (G == 0 || C == 0) return VPF_OK;
+  dim3 grid(G, ceil_div(C, 128));
+  if (dout_bf16) group_max_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16 *)dout, argmax, (bf16 *)dx_bf16, accumulate, S, C);
+  else group_max_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float *)dout, argmax, (bf16 *)dx_bf16, accumulate, S, C);
+  return check_launch("group_max_bwd_kernel");
+}
+
+int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream) {
+  VPF_REQUIRE(x && out && argmax, "token_pool_fwd: null pointer");
+  if (B == 0) return VPF_OK;
+  token_pool_fwd_kernel<<<dim3(B, ceil_div(D, 128)), 128, 0, (cudaStream_t)stream>>>(x, out, argmax, L, D);
+  return check_launch("token_pool_fwd_kernel");
+}
+
+int vpf_token_pool_bwd(const float *dout, const int *argmax, float *dx, int B, int L, int D, void *stream) {
+  VPF_REQUIRE(dout && dx && argmax, "token_pool_bwd: null pointer");
+  if (B == 0) return VPF_OK;
+  token_pool_bwd_kernel<<<dim3(B, ceil_div(D, 128)), 128, 0, (cudaStream_t)stream>>>(dout, argmax, dx, L, D);
+  return check_launch("token_pool_bwd_kernel");
+}
+
+int vpf_linear3_fwd(const float *p, int ldp, const float *w, const float *b, const float *scale, const float *shift,
+                    void *pre_bf16, void *act_bf16, int act, long long R, int Co, void *stream) {
+  VPF_REQUIRE(p && w && b && (pre_bf16 || act_bf16), "linear3_fwd: null pointer");
+  VPF_REQUIRE((scale == nullptr) == (shift == nullptr), "linear3_fwd: scale/shift must come together");
+  if (R == 0) return VPF_OK;
+  linear3_fwd_kernel<<<grid_for((size_t)R * Co), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, scale, shift, (bf16 *)pre_bf16, (bf16 *)act_bf16, act, R, Co);
+  return check_launch("linear3_fwd_kernel");
+}
+
+int vpf_linear3_stats(const float *p, int ldp, const float *w, const float *b, double *stats, long long R, int Co, void *stream) {
+  VPF_REQUIRE(p && w && b && stats, "linear3_stats: null pointer");
+  if (R == 0) return VPF_OK;
+  const int rpc = rows_per_cta_for(R);
+  linear3_stats_kernel<<<(unsigned)ceil_div(R, (long long)rpc), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, stats, R, Co, rpc);
+  return check_launch("linear3_stats_kernel");
+}
+
+int vpf_linear3_bwd(const void *dy, int dy_bf16, const float *p, int ldp, float *dW, float *db, long long R, int Co, void *stream) {
+  VPF_REQUIRE(dy && p && dW && db, "linear3_bwd: null pointer");
+  if (R == 0) return VPF_OK;
+  const int rpc = rows_per_cta_for(R);
+  const unsigned grid = (unsigned)ceil_div(R, (long long)rpc);
+  if (dy_bf16) linear3_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, p, ldp, dW, db, R, Co, rpc);
+  else linear3_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)dy, p, ldp, dW, db, R, Co, rpc);
+  return check_launch("linear3_bwd_kernel");
+}
+
+int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float *w, const float *b, const float *scale,
+                       const float *shift, const float *mean, const float *rstd, double *red, float *dW, float *db,
+                       float *dgamma, float *dbeta, long long R, int Co, void *stream) {
+  VPF_REQUIRE(dh_bf16 && p && w && b && scale && shift && mean && rstd && red && dW && db && dgamma && dbeta, "linear3_bn_bwd: null pointer");
+  if (R == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VPF_CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * Co, st));
+  const int rpc = rows_per_cta_for(R);
+  const unsigned grid = (unsigned)ceil_div(R, (long long)rpc);
+  linear3_bn_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+  VPF_TRY(check_launch("linear3_bn_bwd_kernel<1>"));
+  linear3_bn_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+  VPF_TRY(check_launch("linear3_bn_bwd_kernel<2>"));
+  bn_param_grad_kernel<<<ceil_div(Co, 128), 128, 0, st>>>(red, dgamma, dbeta, Co);
+  return check_launch("bn_param_grad_kernel");
+}
+
+int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, void *stream) {
+  VPF_REQUIRE(img && out_bf16, "patchify: null pointer");
+  VPF_REQUIRE(P > 0 && H % P == 0 && W % P == 0, "patchify: image %dx%d not divisible by patch %d", H, W, P);
+  const size_t total = (size_t)B * H * W * Ci;
+  if (total == 0) return VPF_OK;
+  patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (bf16 *)out_bf16, H, W, Ci, P, total);
+  return check_launch("patchify_kernel");
+}
+
+int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream) {
+  VPF_REQUIRE(a && out, "add_scale: null pointer");
+  if (n == 0) return VPF_OK;
+  add_scale_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(a, b, out, alpha, (size_t)n);
+  return check_launch("add_scale_kernel");
+}
+
+}  // extern "C"

@@ -57,3 +57,227 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, lda=None,
     _lib.call("vpf_gemm_bf16", _vp(a.data_ptr()), _i(int(a_mn)), _i(lda), _vp(b.data_ptr()), _i(int(b_mn)), _i(ldb),
               _i(M), _i(N), _i(K), _i(splits), ctypes.byref(e), _lib.stream_ptr())
     return out
+
+
+# ----------------------------------------------------------------------------- helpers
+_ll = ctypes.c_longlong
+_u = ctypes.c_uint
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _p(t):
+    return _vp(0 if t is None else t.data_ptr())
+
+
+def _isbf(t):
+    return _i(int(t.dtype == BF16))
+
+
+def _s():
+    return _lib.stream_ptr()
+
+
+def zeros_(t):
+    _lib.call("vpf_fill_zero", _p(t), _ll(t.numel() * t.element_size()), _s())
+    return t
+
+
+def cast_bf16(x, out=None):
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=BF16, device=x.device) if out is None else out
+    _lib.call("vpf_cast_bf16", _p(x), _p(out), _ll(x.numel()), _s())
+    return out
+
+
+def add_scale(a, b, alpha, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _lib.call("vpf_add_scale", _p(a), _p(b), _p(out), _f(alpha), _ll(a.numel()), _s())
+    return out
+
+
+# ----------------------------------------------------------------------------- attention
+def attention_fwd(q, k, v, B, H, Lq, Lk, scale, drop_p=0.0, seed=None, op_id=0):
+    """q: [B*Lq, >=H*64] view (row stride = q.stride(0)); k, v: views of one buffer with the same row stride."""
+    assert k.stride(0) == v.stride(0)
+    o = torch.empty((B * Lq, H * 64), dtype=BF16, device=q.device)
+    lse = torch.empty((B * H, Lq), dtype=F32, device=q.device)
+    _lib.call("vpf_attention_fwd", _p(q), _i(q.stride(0)), _p(k), _p(v), _i(k.stride(0)), _p(o), _i(o.stride(0)),
+              _p(lse), _i(B), _i(H), _i(Lq), _i(Lk), _i(64), _f(scale), _f(drop_p), _p(seed), _u(op_id), _s())
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Lq, Lk, scale, drop_p=0.0, seed=None, op_id=0):
+    assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0)
+    delta = torch.empty((B * H, Lq), dtype=F32, device=q.device)
+    _lib.call("vpf_attention_bwd", _p(q), _i(q.stride(0)), _p(k), _p(v), _i(k.stride(0)), _p(o), _i(o.stride(0)),
+              _p(do), _i(do.stride(0)), _p(lse), _p(delta), _p(dq), _i(dq.stride(0)), _p(dk), _p(dv),
+              _i(dk.stride(0)), _i(B), _i(H), _i(Lq), _i(Lk), _i(64), _f(scale), _f(drop_p), _p(seed), _u(op_id), _s())
+
+
+# ----------------------------------------------------------------------------- norms
+def layernorm_fwd(x, gamma, beta, *, add=None, want_xsum=False, relu=False, eps=1e-5):
+    T, D = x.shape
+    y = torch.empty((T, D), dtype=BF16, device=x.device)
+    mean = torch.empty(T, dtype=F32, device=x.device)
+    rstd = torch.empty(T, dtype=F32, device=x.device)
+    xsum = torch.empty((T, D), dtype=F32, device=x.device) if want_xsum else None
+    add_rows = 0 if add is None else add.numel() // D
+    _lib.call("vpf_layernorm_fwd", _p(x), _isbf(x), _p(add), _i(add_rows), _p(xsum), _p(gamma), _p(beta), _p(y),
+              _p(mean), _p(rstd), _i(T), _i(D), _f(eps), _i(int(relu)), _s())
+    return y, mean, rstd, xsum
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, y_relu=None, dres=None, dgamma=None, dbeta=None, dpos=None,
+                  out_dtype=F32):
+    T, D = x.shape
+    dx = torch.empty((T, D), dtype=out_dtype, device=x.device)
+    pos_rows = 0 if dpos is None else dpos.numel() // D
+    _lib.call("vpf_layernorm_bwd", _p(dy), _isbf(dy), _p(x), _isbf(x), _p(y_relu), _p(mean), _p(rstd), _p(gamma),
+              _p(dres), _p(dx), _isbf(dx), _p(dgamma), _p(dbeta), _p(dpos), _i(pos_rows), _i(T), _i(D), _s())
+    return dx
+
+
+def dropout_grad(g, p, seed, op_id, colsum=None):
+    T, N = g.shape
+    out = torch.empty((T, N), dtype=BF16, device=g.device)
+    _lib.call("vpf_dropout_grad", _p(g), _p(out), _p(colsum), _f(p), _p(seed), _u(op_id), _i(T), _i(N), _s())
+    return out
+
+
+def colsum(x, *, sum64=None, sumsq64=None, sum32=None):
+    R, C = x.shape
+    _lib.call("vpf_colsum", _p(x), _isbf(x), _p(sum64), _p(sumsq64), _p(sum32), _ll(R), _i(C), _s())
+
+
+class BNState:
+    """Folded affine + saved statistics of one BatchNorm1d call."""
+    __slots__ = ("scale", "shift", "mean", "rstd", "R")
+
+
+def bn_stats_finalize(stats, R, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    C = gamma.numel()
+    st = BNState()
+    buf = torch.empty((4, C), dtype=F32, device=gamma.device)
+    st.scale, st.shift, st.mean, st.rstd, st.R = buf[0], buf[1], buf[2], buf[3], R
+    _lib.call("vpf_bn_finalize", _p(stats), _ll(R), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+              _f(momentum), _f(eps), _i(int(training)), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd), _i(C), _s())
+    return st
+
+
+def bn_forward(x, gamma, beta, running_mean, running_var, training, relu, out_dtype=BF16, momentum=0.1, eps=1e-5):
+    R, C = x.shape
+    stats = None
+    if training:
+        stats = zeros_(torch.empty(2 * C, dtype=torch.float64, device=x.device))
+        colsum(x, sum64=stats[:C], sumsq64=stats[C:])
+    st = bn_stats_finalize(stats, R, gamma, beta, running_mean, running_var, training, momentum, eps)
+    y = torch.empty((R, C), dtype=out_dtype, device=x.device)
+    _lib.call("vpf_bn_apply", _p(x), _isbf(x), _p(st.scale), _p(st.shift), _p(y), _isbf(y), _i(int(relu)), _ll(R), _i(C), _s())
+    return y, st
+
+
+def bn_backward(dy, x, st, relu, dgamma, dbeta, out_dtype=BF16):
+    R, C = x.shape
+    red = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+    dx = torch.empty((R, C), dtype=out_dtype, device=x.device)
+    _lib.call("vpf_bn_bwd", _p(dy), _isbf(dy), _p(x), _isbf(x), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd),
+              _i(int(relu)), _p(red), _p(dx), _isbf(dx), _p(dgamma), _p(dbeta), _ll(R), _i(C), _s())
+    return dx
+
+
+# ----------------------------------------------------------------------------- pooling / thin ops
+def group_max_fwd(x, G, S, C, want_bf16=True, want_f32=False):
+    ob = torch.empty((G, C), dtype=BF16, device=x.device) if want_bf16 else None
+    of = torch.empty((G, C), dtype=F32, device=x.device) if want_f32 else None
+    am = torch.empty((G, C), dtype=torch.uint8, device=x.device)
+    _lib.call("vpf_group_max_fwd", _p(x), _p(ob), _p(of), _p(am), _i(G), _i(S), _i(C), _s())
+    return ob, of, am
+
+
+def group_max_bwd(dout, argmax, G, S, C, dx=None):
+    accumulate = dx is not None
+    if dx is None:
+        dx = torch.empty((G * S, C), dtype=BF16, device=dout.device)
+    _lib.call("vpf_group_max_bwd", _p(dout), _isbf(dout), _p(argmax), _p(dx), _i(int(accumulate)), _i(G), _i(S), _i(C), _s())
+    return dx
+
+
+def token_pool_fwd(x, B, L, D):
+    out = torch.empty((B, 2 * D), dtype=F32, device=x.device)
+    am = torch.empty((B, D), dtype=torch.int32, device=x.device)
+    _lib.call("vpf_token_pool_fwd", _p(x), _p(out), _p(am), _i(B), _i(L), _i(D), _s())
+    return out, am
+
+
+def token_pool_bwd(dout, am, B, L, D):
+    dx = torch.empty((B * L, D), dtype=F32, device=dout.device)
+    _lib.call("vpf_token_pool_bwd", _p(dout), _p(am), _p(dx), _i(B), _i(L), _i(D), _s())
+    return dx
+
+
+def linear3_fwd(p, ldp, w, b, R, *, scale=None, shift=None, want_pre=False, act=None):
+    Co = w.shape[0]
+    pre = torch.empty((R, Co), dtype=BF16, device=p.device) if want_pre else None
+    ao = torch.empty((R, Co), dtype=BF16, device=p.device) if act is not None else None
+    _lib.call("vpf_linear3_fwd", _p(p), _i(ldp), _p(w), _p(b), _p(scale), _p(shift), _p(pre), _p(ao),
+              _i(act if act is not None else 0), _ll(R), _i(Co), _s())
+    return pre, ao
+
+
+def linear3_stats(p, ldp, w, b, R):
+    Co = w.shape[0]
+    stats = zeros_(torch.empty(2 * Co, dtype=torch.float64, device=p.device))
+    _lib.call("vpf_linear3_stats", _p(p), _i(ldp), _p(w), _p(b), _p(stats), _ll(R), _i(Co), _s())
+    return stats
+
+
+def linear3_bwd(dy, p, ldp, dW, db, R):
+    _lib.call("vpf_linear3_bwd", _p(dy), _isbf(dy), _p(p), _i(ldp), _p(dW), _p(db), _ll(R), _i(dW.shape[0]), _s())
+
+
+def linear3_bn_bwd(dh, p, ldp, w, b, st, dW, db, dgamma, dbeta, R):
+    Co = w.shape[0]
+    red = torch.empty(2 * Co, dtype=torch.float64, device=p.device)
+    _lib.call("vpf_linear3_bn_bwd", _p(dh), _p(p), _i(ldp), _p(w), _p(b), _p(st.scale), _p(st.shift), _p(st.mean),
+              _p(st.rstd), _p(red), _p(dW), _p(db), _p(dgamma), _p(dbeta), _ll(R), _i(Co), _s())
+
+
+def patchify(img, P):
+    B, H, W, Ci = img.shape
+    out = torch.empty((B * (H // P) * (W // P), P * P * Ci), dtype=BF16, device=img.device)
+    _lib.call("vpf_patchify", _p(img), _p(out), _i(B), _i(H), _i(W), _i(Ci), _i(P), _s())
+    return out
+
+
+# ----------------------------------------------------------------------------- loss / optimiser
+def l2norm_rows(x):
+    n, D = x.shape
+    z = torch.empty_like(x)
+    norm = torch.empty(n, dtype=F32, device=x.device)
+    _lib.call("vpf_l2norm_rows", _p(x), _p(z), _p(norm), _i(n), _i(D), _s())
+    return z, norm
+
+
+def ntxent_fwd(zr, zc, b_local, col_offset, half, temperature, loss_out):
+    n_r, D = zr.shape
+    lse = torch.empty(n_r, dtype=F32, device=zr.device)
+    _lib.call("vpf_ntxent_fwd", _p(zr), _i(n_r), _p(zc), _i(zc.shape[0]), _i(D), _i(b_local), _i(col_offset), _i(half),
+              _f(temperature), _p(lse), _p(loss_out), _s())
+    return lse
+
+
+def ntxent_bwd(zr, norm, zc, lse_all, b_local, col_offset, half, temperature, gscale, upstream=None):
+    n_r, D = zr.shape
+    dx = torch.empty((n_r, D), dtype=F32, device=zr.device)
+    _lib.call("vpf_ntxent_bwd", _p(zr), _p(norm), _i(n_r), _p(zc), _p(lse_all), _i(zc.shape[0]), _i(D), _i(b_local),
+              _i(col_offset), _i(half), _f(temperature), _f(gscale), _p(upstream), _p(dx), _s())
+    return dx
+
+
+def adamw(p, g, m, v, shadow, lr_ptr, step_ptr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+    _lib.call("vpf_adamw", _p(p), _p(g), _p(m), _p(v), _p(shadow), _ll(p.numel()), _p(lr_ptr), _f(beta1), _f(beta2),
+              _f(eps), _f(weight_decay), _p(step_ptr), _f(grad_scale), _s())
+
+
+def step_advance(state):
+    _lib.call("vpf_step_advance", _p(state), _s())
