@@ -189,6 +189,8 @@ int vpf_group_max_fwd(const void *x_bf16, void *out_bf16, float *out_f32, uint8_
                       int G, int S, int C, void *stream);
 int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, void *dx_bf16,
                       int accumulate, int G, int S, int C, void *stream);
+/* sum over the S rows of each group (gradient of the broadcast in utils.py:183). */
+int vpf_group_sum(const void *x_bf16, void *out_bf16, float *out_f32, int G, int S, int C, void *stream);
 /* cat(x.max(1)[0], x.mean(1)), partseg.py:547. */
 int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream);
 int vpf_token_pool_bwd(const float *dout, const int *argmax, float *dx, int B, int L, int D, void *stream);

@@ -1,0 +1,173 @@
+"""Plain PyTorch fp32/fp64 CPU restatement of the floating-point half of the hot path -- TEST INFRASTRUCTURE ONLY.
+
+Functional style over a reference-layout state_dict (same keys as the reference's modules), so the
+same weights drive this oracle, the real reference (tests/make_golden_model.py, build container only)
+and the CUDA product.  Autograd of this restatement is the gradient oracle.
+
+Each function cites the reference lines it restates (paths relative to the upstream repo root).
+Pinned against the real reference by tests/golden/model_*.npz (tests/test_oracle_golden.py).
+`ntxent` restates the un-vendored lightly==1.1.21 package => that function is "parity unpinned"
+(no reference source or test vector exists in-tree).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import tokenizer as T
+
+
+def _lin(sd, k, x, bias=True):
+    return F.linear(x, sd[k + ".weight"], sd[k + ".bias"] if bias and (k + ".bias") in sd else None)
+
+
+def _ln(sd, k, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[k + ".weight"], sd[k + ".bias"], 1e-5)
+
+
+def _bn(sd, k, x, training, running_out=None):
+    """nn.BatchNorm1d on [R, C] (or [B, C, L] flattened by the caller): train = batch stats (biased var), eps 1e-5."""
+    if training:
+        mean = x.mean(0)
+        var = x.var(0, unbiased=False)
+        if running_out is not None:   # momentum 0.1, unbiased variance into running_var
+            running_out[k + ".running_mean"] = 0.9 * sd[k + ".running_mean"] + 0.1 * mean.detach()
+            running_out[k + ".running_var"] = 0.9 * sd[k + ".running_var"] + 0.1 * x.var(0, unbiased=True).detach()
+    else:
+        mean, var = sd[k + ".running_mean"], sd[k + ".running_var"]
+    return (x - mean) / torch.sqrt(var + 1e-5) * sd[k + ".weight"] + sd[k + ".bias"]
+
+
+def mha(sd, k, xq, xkv, H):
+    """MultiHeadAttention.forward, partseg.py:53-86 (pad_mask None, dropout off)."""
+    q, kk, v = _lin(sd, k + ".q_proj", xq, False), _lin(sd, k + ".k_proj", xkv, False), _lin(sd, k + ".v_proj", xkv, False)
+    B, Lq, D = q.shape
+    Lk = kk.shape[1]
+    dh = D // H
+    q = q.view(B, Lq, H, dh).transpose(1, 2)
+    kk = kk.view(B, Lk, H, dh).transpose(1, 2)
+    v = v.view(B, Lk, H, dh).transpose(1, 2)
+    attn = (q @ kk.transpose(-1, -2)) * dh ** -0.5
+    attn = attn.softmax(-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, Lq, D)
+    return _lin(sd, k + ".o_proj", o)
+
+
+def mlp(sd, k, x):
+    """MLP, partseg.py:191-198: LN, Linear, exact GELU, Linear."""
+    return _lin(sd, k + ".3", F.gelu(_lin(sd, k + ".1", _ln(sd, k + ".0", x))))
+
+
+def ca_layer(sd, k, xq, xkv, H):
+    """CrossAttentionLayer, partseg.py:144-167 with Residual (:201-213), dropout off."""
+    a = k + ".0.module"
+    x = mha(sd, a + ".attention", _ln(sd, a + ".q_norm", xq), _ln(sd, a + ".kv_norm", xkv), H) + xq
+    return mlp(sd, k + ".1.module", x) + x
+
+
+def sa_layer(sd, k, x, H):
+    """SelfAttentionLayer, partseg.py:170-188."""
+    a = k + ".0.module"
+    xn = _ln(sd, a + ".norm", x)
+    x = mha(sd, a + ".attention", xn, xn, H) + x
+    return mlp(sd, k + ".1.module", x) + x
+
+
+def encoder(sd, k, group_embs, pos_embs, pts_embs, H, n_sa):
+    """Encoder.forward, partseg.py:314-342 (one cross-attention layer, modal_prior=True)."""
+    x = ca_layer(sd, k + ".cross_attn_1", group_embs + pos_embs, pts_embs, H)
+    for i in range(n_sa):
+        x = sa_layer(sd, f"{k}.sa_layers.{i}", x + pos_embs, H)
+    return x
+
+
+def group2emb(sd, k, nb, training, running_out=None):
+    """Group2Emb.forward, utils.py:168-189.  nb [B,G,S,3] -> [B,G,D]."""
+    bs, g, n, _ = nb.shape
+    x = nb.reshape(bs * g * n, 3)
+    x = F.linear(x, sd[k + ".first_conv.0.weight"][:, :, 0], sd[k + ".first_conv.0.bias"])
+    x = F.relu(_bn(sd, k + ".first_conv.1", x, training, running_out))
+    x = F.linear(x, sd[k + ".first_conv.3.weight"][:, :, 0], sd[k + ".first_conv.3.bias"])  # [R,128]
+    xg = x.view(bs * g, n, 128).max(1, keepdim=True)[0].expand(-1, n, -1)
+    x = torch.cat([xg, x.view(bs * g, n, 128)], -1).reshape(bs * g * n, 256)
+    x = F.linear(x, sd[k + ".second_conv.0.weight"][:, :, 0], sd[k + ".second_conv.0.bias"])
+    x = F.relu(_bn(sd, k + ".second_conv.1", x, training, running_out))
+    x = F.linear(x, sd[k + ".second_conv.3.weight"][:, :, 0], sd[k + ".second_conv.3.bias"])
+    D = x.shape[-1]
+    return x.view(bs * g, n, D).max(1)[0].view(bs, g, D)
+
+
+def input_adapter(sd, k, pts):
+    """PointCloudInputAdapter.forward, classifier.py:31-50."""
+    m = k + ".point_mlp"
+    return _lin(sd, m + ".3", F.relu(_ln(sd, m + ".1", _lin(sd, m + ".0", pts))))
+
+
+def position_emb(sd, k, center):
+    """partseg.py:498-501."""
+    return _lin(sd, k + ".2", F.gelu(_lin(sd, k + ".0", center)))
+
+
+def latent_head(sd, k, x, training, running_out=None):
+    """partseg.py:519-525 on backbone feats [B,2D]."""
+    x = F.relu(_bn(sd, k + ".0", x, training, running_out))
+    x = F.linear(x, sd[k + ".2.weight"])
+    x = F.relu(_bn(sd, k + ".3", x, training, running_out))
+    return F.linear(x, sd[k + ".5.weight"])
+
+
+def pc_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=None):
+    """CrossFormer_pc_mp.forward, partseg.py:527-550, with the tokenizer pinned as in oracle/tokenizer_oracle.c."""
+    pts_embs = input_adapter(sd, "input_adapter", pts)
+    nb, ce = T.divide_patches(pts.detach().numpy(), G, S, np.asarray(start_idx))
+    nb, ce = torch.from_numpy(nb).to(pts.dtype), torch.from_numpy(ce).to(pts.dtype)
+    group_embs = group2emb(sd, "group2emb", nb, training, running_out)
+    pos_embs = position_emb(sd, "position_emb", ce)
+    x = encoder(sd, "encoder", group_embs, pos_embs, pts_embs, H, n_sa)
+    backbone = torch.cat([x.max(1)[0], x.mean(1)], 1)
+    return latent_head(sd, "latent_head", backbone, training, running_out), backbone
+
+
+def patch2emb(sd, k, imgs, patch):
+    """partseg.py:631-634: Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)' + Linear."""
+    B, Hh, Ww, C = imgs.shape
+    x = imgs.view(B, Hh // patch, patch, Ww // patch, patch, C).permute(0, 1, 3, 2, 4, 5).reshape(B, -1, patch * patch * C)
+    return _lin(sd, k + ".1", x)
+
+
+def img_forward(sd, imgs, patch, H, n_sa, training=True, running_out=None):
+    """CrossFormer_img_mp.forward, partseg.py:661-680."""
+    e = patch2emb(sd, "patch2emb", imgs, patch)
+    x = encoder(sd, "encoder", e, sd["position_emb"], e, H, n_sa)
+    backbone = torch.cat([x.max(1)[0], x.mean(1)], 1)
+    return latent_head(sd, "latent_head", backbone, training, running_out), backbone
+
+
+def ntxent(out0, out1, temperature=0.1):
+    """lightly==1.1.21 lightly/loss/ntx_ent_loss.py NTXentLoss.forward (memory bank off) -- PARITY UNPINNED.
+    Call sites: pretrain.py:155,196,202."""
+    out0, out1 = F.normalize(out0, dim=1), F.normalize(out1, dim=1)
+    b = out0.shape[0]
+    z = torch.cat([out0, out1], 0)
+    logits = torch.einsum("nc,mc->nm", z, z) / temperature
+    logits = logits[~torch.eye(2 * b, dtype=torch.bool)].view(2 * b, -1)
+    labels = torch.cat([torch.arange(b) + b - 1, torch.arange(b)])
+    return F.cross_entropy(logits, labels)
+
+
+def ntxent_closed_form(out0, out1, temperature=0.1):
+    """mean_i [ logsumexp_{j != i} s_ij - s_{i,pos(i)} ] -- the algebraic definition the restatement must equal."""
+    z = torch.cat([F.normalize(out0, dim=1), F.normalize(out1, dim=1)], 0).double()
+    n = z.shape[0]
+    s = z @ z.t() / temperature
+    s_masked = s.masked_fill(torch.eye(n, dtype=torch.bool), -float("inf"))
+    pos = torch.cat([torch.arange(n // 2) + n // 2, torch.arange(n // 2)])
+    return (torch.logsumexp(s_masked, 1) - s[torch.arange(n), pos]).mean()
+
+
+def pretrain_loss(pc_feats, img_feats, cmid_weight=1.0, temperature=0.1):
+    """Loss composition of pretrain.py:189-207 (modality 'both')."""
+    b = pc_feats.shape[0] // 2
+    t1, t2 = pc_feats[:b], pc_feats[b:]
+    imid = ntxent(t1, t2, temperature)
+    cmid = ntxent((t1 + t2) / 2, img_feats, temperature)
+    return imid + cmid_weight * cmid, imid, cmid

@@ -56,3 +56,61 @@ TOKENIZER_CASES = [
     ("allsame_128_16", "allsame", 1, 128, 16, 32, 18),
     ("odd_333_40_8", "randn", 3, 333, 40, 8, 19),     # ragged N, non-default S
 ]
+
+
+# ------------------------------------------------------------------------------------------ model fixtures
+MODEL_CASES = {
+    # name: dict(D, H, n_sa, G, S, N, MR, b (pairs), img)
+    "small": dict(D=128, H=2, n_sa=2, G=32, S=8, N=128, MR=2, b=6, img=144, patch=12, seed=21),
+    "cfgA": dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, b=4, img=144, patch=12, seed=22),
+}
+
+
+def build_models(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
+    """Construct (pc_model, img_model) with the kwargs of the reference's utils.build_model (utils.py:115-148),
+    from `pkg` = 'vipformer_b200' (the product mirror) or 'vipformer' (the real reference, build container only)."""
+    import importlib
+
+    import torch
+
+    pcmod = importlib.import_module(pkg + ".model.pointcloud")
+    torch.manual_seed(cfg["seed"])
+    ad = pcmod.PointCloudInputAdapter(pointcloud_shape=(cfg["N"], 3), num_input_channels=cfg["D"])
+    common = dict(num_latent_channels=cfg["D"], num_cross_attention_layers=1, num_cross_attention_heads=cfg["H"],
+                  num_self_attention_layers=cfg["n_sa"], num_self_attention_heads=cfg["H"],
+                  mlp_widen_factor=cfg["MR"], max_dpr=0.0, atten_drop=atten_drop, mlp_drop=mlp_drop, modal_prior=True)
+    pc = pcmod.CrossFormer_pc_mp(input_adapter=ad, num_latents=cfg["G"], group_size=cfg["S"], **common)
+    im = pcmod.CrossFormer_img_mp(img_height=cfg["img"], img_width=cfg["img"], patch_size=cfg["patch"], **common)
+    return pc, im
+
+
+def perturb_state_dict(sd, seed):
+    """Deterministic perturbation so LayerNorm/BatchNorm affine terms and biases are not at their trivial init."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        if v.dtype.is_floating_point:
+            noise = torch.randn(v.shape, generator=g)
+            if k.endswith("running_var"):
+                v = v + 0.1 * noise.abs()
+            else:
+                v = v + 0.02 * noise
+        out[k] = v.clone()
+    for k in list(out.keys()):   # cross_attn_1 / cross_attn_n alias ONE module (partseg.py:295-300): keep them equal
+        if ".cross_attn_n." in k:
+            out[k] = out[k.replace(".cross_attn_n.", ".cross_attn_1.")].clone()
+    return out
+
+
+def model_inputs(cfg):
+    import torch
+
+    b = cfg["b"]
+    pts = np.concatenate([make_clouds("randn", b, cfg["N"], cfg["seed"] + 1), make_clouds("randn", b, cfg["N"], cfg["seed"] + 2)], 0)
+    start = make_start(2 * b, cfg["N"], cfg["seed"])
+    g = torch.Generator().manual_seed(cfg["seed"] + 3)
+    imgs = torch.randn((b, cfg["img"], cfg["img"], 3), generator=g)
+    return torch.from_numpy(pts), start, imgs

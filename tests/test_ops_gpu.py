@@ -261,7 +261,8 @@ def test_linear3_family():
     dg, dbt = torch.zeros(Co, device="cuda"), torch.zeros(Co, device="cuda")
     ops.linear3_bn_bwd(dh, p, 3, w, b, st, dW, db, dg, dbt, R)
     assert relfro(dW, wr.grad) < 5e-3
-    close(db, br.grad, tol=5e-2)   # ~0 analytically (BN removes the mean): absolute check against the scale of dW
+    # db is analytically 0 (BN removes the mean): only noise on the scale of dW's rounding is allowed
+    assert db.abs().max().item() < 1e-3 * wr.grad.abs().max().item() and br.grad.abs().max().item() < 1e-3 * wr.grad.abs().max().item()
     assert relfro(dg, bn.weight.grad) < 5e-3 and relfro(dbt, bn.bias.grad) < 5e-3
 
 

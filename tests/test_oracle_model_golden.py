@@ -1,0 +1,79 @@
+"""CPU: pin oracle/model_ref.py (the floating-point oracle) against golden vectors made from the REAL reference.
+Tolerance: both sides are fp32 CPU PyTorch evaluating the same formulae in (slightly) different op order -> rel 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _synth
+from oracle import model_ref as M
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def oracle_run(cfg, dtype=torch.float32):
+    """Shared with the GPU tests: product-mirror init (identical to the reference's, asserted by make_golden_model.py)
+    -> perturbed state_dicts -> oracle forward/loss/backward."""
+    pc, im = _synth.build_models(cfg)
+    sd_pc = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(pc.state_dict(), cfg["seed"] + 10).items()}
+    sd_im = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(im.state_dict(), cfg["seed"] + 11).items()}
+    pnames = [k for k, _ in pc.named_parameters()]
+    inames = [k for k, _ in im.named_parameters()]
+    for k in pnames:
+        sd_pc[k] = sd_pc[k].clone().requires_grad_(True)
+    for k in inames:
+        sd_im[k] = sd_im[k].clone().requires_grad_(True)
+    for sd in (sd_pc, sd_im):   # cross_attn_1 and cross_attn_n are ONE module in the reference (partseg.py:295-300)
+        for k in list(sd.keys()):
+            if ".cross_attn_n." in k:
+                sd[k.replace(".cross_attn_n.", ".cross_attn_1.")] = sd[k]
+    pts, start, imgs = _synth.model_inputs(cfg)
+    run_pc, run_im = {}, {}
+    pc_feats, pc_back = M.pc_forward(sd_pc, pts.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, run_pc)
+    im_feats, im_back = M.img_forward(sd_im, imgs.to(dtype), cfg["patch"], cfg["H"], cfg["n_sa"], True, run_im)
+    total, imid, cmid = M.pretrain_loss(pc_feats, im_feats)
+    total.backward()
+    return dict(sd_pc=sd_pc, sd_im=sd_im, pnames=pnames, inames=inames, pc_feats=pc_feats.detach(), pc_back=pc_back.detach(),
+                im_feats=im_feats.detach(), im_back=im_back.detach(), loss=(total.item(), imid.item(), cmid.item()),
+                run_pc=run_pc, run_im=run_im, inputs=(pts, start, imgs))
+
+
+@pytest.mark.parametrize("name", ["small", "cfgA"])
+def test_model_oracle_matches_reference(name, golden_dir):
+    cfg = _synth.MODEL_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    torch.set_num_threads(8)
+    o = oracle_run(cfg)
+    assert _rel(o["pc_feats"], g["pc_feats"]) < 1e-4
+    assert _rel(o["pc_back"], g["pc_backbone"]) < 1e-4
+    assert _rel(o["im_feats"], g["img_feats"]) < 1e-4
+    assert _rel(o["im_back"], g["img_backbone"]) < 1e-4
+    assert np.allclose(o["loss"], g["loss"], rtol=1e-4, atol=1e-5)
+    for tag, sd, names, run in (("pc", o["sd_pc"], o["pnames"], o["run_pc"]), ("img", o["sd_im"], o["inames"], o["run_im"])):
+        assert list(g[f"{tag}_grad_names"]) == names
+        norms = np.array([sd[k].grad.double().norm().item() for k in names])
+        ref = g[f"{tag}_grad_norms"]
+        # biases in front of a train-mode BatchNorm have analytically ZERO gradient: only fp32 noise (absolute tolerance)
+        assert np.all(np.abs(norms - ref) <= 2e-3 * ref + 1e-5 * ref.max()), f"{tag} gradient norms differ from the reference"
+        for key in g.files:
+            if key.startswith(f"{tag}_grad::"):
+                k = key.split("::")[1]
+                assert _rel(sd[k].grad, g[key]) < 2e-3 or np.abs(g[key]).max() < 1e-5 * g[f"{tag}_grad_norms"].max(), k
+            if key.startswith(f"{tag}_buf::"):
+                k = key.split("::")[1]
+                assert _rel(run[k], g[key]) < 1e-4, k
+
+
+def test_ntxent_restatement_equals_closed_form():
+    """lightly is third-party and absent: the restated CE-over-masked-logits form is pinned only by its algebraic
+    definition (parity unpinned)."""
+    g = torch.Generator().manual_seed(0)
+    for b, D in ((4, 16), (55, 256)):
+        x0, x1 = torch.randn((b, D), generator=g), torch.randn((b, D), generator=g)
+        a = M.ntxent(x0.double(), x1.double()).item()
+        c = M.ntxent_closed_form(x0.double(), x1.double()).item()
+        assert abs(a - c) < 1e-9

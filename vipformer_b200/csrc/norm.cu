@@ -391,6 +391,8 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
   else if (!dy_bf16 && !x_bf16 && !dx_bf16) BNB(float, float, float)
   else if (dy_bf16 && !x_bf16 && dx_bf16) BNB(bf16, float, bf16)
   else if (!dy_bf16 && x_bf16 && dx_bf16) BNB(float, bf16, bf16)
+  else if (dy_bf16 && !x_bf16 && !dx_bf16) BNB(bf16, float, float)
+  else if (!dy_bf16 && !x_bf16 && dx_bf16) BNB(float, float, bf16)
   else return fail(VPF_EINVAL, "bn_bwd: unsupported dtype combination");
 #undef BNB
   return check_launch("bn_bwd_apply_kernel");

@@ -52,6 +52,19 @@ group_max_bwd_kernel(const Tdo *__restrict__ dout, const uint8_t *__restrict__ a
   }
 }
 
+// sum over the S rows of each group: x bf16 [G,S,C] -> out_bf16 [G,C] (optional) and out_f32 (optional)
+__global__ void __launch_bounds__(128)
+group_sum_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ out_bf16, float *__restrict__ out_f32, int S, int C) {
+  const int g = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const bf16 *p = x + (size_t)g * S * C + c;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += __bfloat162float(p[(size_t)s * C]);
+  const size_t o = (size_t)g * C + c;
+  if (out_bf16) out_bf16[o] = __float2bfloat16(acc);
+  if (out_f32) out_f32[o] = acc;
+}
+
 // --------------------------------------------------------------- token pool
 // x fp32 [B,L,D] -> out fp32 [B,2D] = (max_l || mean_l); argmax int32 [B,D]
 __global__ void __launch_bounds__(128)
@@ -234,6 +247,13 @@ int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, vo
   if (dout_bf16) group_max_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16 *)dout, argmax, (bf16 *)dx_bf16, accumulate, S, C);
   else group_max_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float *)dout, argmax, (bf16 *)dx_bf16, accumulate, S, C);
   return check_launch("group_max_bwd_kernel");
+}
+
+int vpf_group_sum(const void *x_bf16, void *out_bf16, float *out_f32, int G, int S, int C, void *stream) {
+  VPF_REQUIRE(x_bf16 && (out_bf16 || out_f32), "group_sum: null pointer");
+  if (G == 0 || C == 0) return VPF_OK;
+  group_sum_kernel<<<dim3(G, ceil_div(C, 128)), 128, 0, (cudaStream_t)stream>>>((const bf16 *)x_bf16, (bf16 *)out_bf16, out_f32, S, C);
+  return check_launch("group_sum_kernel");
 }
 
 int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream) {

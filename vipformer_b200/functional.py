@@ -1,0 +1,282 @@
+"""Forward/backward of the ViPFormer blocks as explicit kernel sequences (no autograd inside).
+
+Every function takes plain tensors and returns (outputs, ctx); the matching *_bwd consumes ctx,
+accumulates parameter gradients IN PLACE into the fp32 grad tensors it is handed (the kernels
+use red.global.add / atomics, so handing in views of one flat gradient buffer is free) and
+returns the input gradients.  `modules.py` wraps these in torch.autograd.Function.
+
+Storage conventions: residual stream and small per-sample tensors fp32; GEMM operands and the big
+per-point / per-group-point activations bf16; all accumulation fp32 (fp64 for BatchNorm sums).
+Reference: vipformer/model/pointcloud/partseg.py:15-342,473-680, utils.py:144-189, classifier.py:25-50.
+"""
+import math
+from types import SimpleNamespace as NS
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_RELU, AUX_GELU_GRAD, BF16, EPI_ATOMIC_ADD, EPI_RESIDUAL, F32
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _wgrad(dy, x, dW, ldc=None):
+    """dW[N_out, K_in] += dy[T, N_out]^T @ x[T, K_in]   (both operands MN-major, split-K, atomic accumulate)."""
+    ops.gemm(dy, x, dW, a_mn=True, b_mn=True, mode=EPI_ATOMIC_ADD, ldc=ldc)
+
+
+def _dgrad(dy, w, out, **kw):
+    """out[T, K_in] = dy[T, N_out] @ w[N_out, K_in]   (B consumed MN-major: no transposed weight copy)."""
+    return ops.gemm(dy, w, out, b_mn=True, **kw)
+
+
+# =============================================================================== MLP (partseg.py:191-198)
+def _mlp_fwd(x1, W, T, D, p_drop, seed, op_id, save):
+    xn2, mean2, rstd2, _ = ops.layernorm_fwd(x1, W.ln2_w, W.ln2_b)
+    F_ = W.w1.shape[0]
+    h = _empty((T, F_), BF16, x1)
+    z = _empty((T, F_), BF16, x1) if save else None
+    ops.gemm(xn2, W.w1, h, bias=W.b1, act=ACT_GELU, out2=z)
+    x2 = _empty((T, D), F32, x1)
+    ops.gemm(h, W.w2, x2, bias=W.b2, mode=EPI_RESIDUAL, resid=x1, drop_p=p_drop, seed=seed, op_id=op_id)
+    return x2, NS(xn2=xn2, mean2=mean2, rstd2=rstd2, h=h, z=z, x1=x1)
+
+
+def _mlp_bwd(dx2, c, W, G, T, D, p_drop, seed, op_id):
+    g2 = ops.dropout_grad(dx2, p_drop, seed, op_id, colsum=G.b2)
+    _wgrad(g2, c.h, G.w2)
+    F_ = W.w1.shape[0]
+    dz = _empty((T, F_), BF16, dx2)
+    _dgrad(g2, W.w2, dz, aux=c.z, aux_mode=AUX_GELU_GRAD)
+    ops.colsum(dz, sum32=G.b1)
+    _wgrad(dz, c.xn2, G.w1)
+    dxn2 = _empty((T, D), F32, dx2)
+    _dgrad(dz, W.w1, dxn2)
+    return ops.layernorm_bwd(dxn2, c.x1, c.mean2, c.rstd2, W.ln2_w, dres=dx2, dgamma=G.ln2_w, dbeta=G.ln2_b)
+
+
+# ============================================================ SelfAttentionLayer (partseg.py:170-188)
+def sa_layer_fwd(x_prev, pos, W, cfg, seed, op_base, save=True):
+    """x_prev fp32 [B*L, D]; pos fp32 [pos_rows, D] (re-added before every layer, Encoder.forward :331-335)."""
+    B, L, D, H = cfg.B, cfg.L, cfg.D, cfg.H
+    T = B * L
+    xn, mean1, rstd1, xin = ops.layernorm_fwd(x_prev, W.ln1_w, W.ln1_b, add=pos, want_xsum=True)
+    qkv = _empty((T, 3 * D), BF16, x_prev)
+    ops.gemm(xn, W.wqkv, qkv)
+    o, lse = ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, cfg.scale, cfg.p_attn, seed, op_base)
+    x1 = _empty((T, D), F32, x_prev)
+    ops.gemm(o, W.wo, x1, bias=W.bo, mode=EPI_RESIDUAL, resid=xin, drop_p=cfg.p_res1, seed=seed, op_id=op_base + 1)
+    x2, cm = _mlp_fwd(x1, W, T, D, cfg.p_res2, seed, op_base + 2, save)
+    ctx = NS(xn=xn, mean1=mean1, rstd1=rstd1, xin=xin, qkv=qkv, o=o, lse=lse, mlp=cm) if save else None
+    return x2, ctx
+
+
+def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos):
+    B, L, D, H = cfg.B, cfg.L, cfg.D, cfg.H
+    T = B * L
+    dx1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2)
+    g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
+    _wgrad(g1, c.o, G.wo)
+    do = _empty((T, D), BF16, dx2)
+    _dgrad(g1, W.wo, do)
+    dqkv = _empty((T, 3 * D), BF16, dx2)
+    qkv = c.qkv
+    ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], c.o, do, c.lse, dqkv[:, :D], dqkv[:, D:2 * D],
+                      dqkv[:, 2 * D:], B, H, L, L, cfg.scale, cfg.p_attn, seed, op_base)
+    _wgrad(dqkv, c.xn, G.wqkv)
+    dxn = _empty((T, D), F32, dx2)
+    _dgrad(dqkv, W.wqkv, dxn)
+    return ops.layernorm_bwd(dxn, c.xin, c.mean1, c.rstd1, W.ln1_w, dres=dx1, dgamma=G.ln1_w, dbeta=G.ln1_b, dpos=dpos)
+
+
+# =========================================================== CrossAttentionLayer (partseg.py:144-167)
+def ca_layer_fwd(xq_prev, pos, kv_in, W, cfg, seed, op_base, save=True):
+    """xq_prev fp32 [B*L, D] (+pos); kv_in bf16 or fp32 [B*Lk, D] (no positional term, Encoder.forward :326)."""
+    B, L, Lk, D, H = cfg.B, cfg.L, cfg.Lk, cfg.D, cfg.H
+    T, Tk = B * L, B * Lk
+    qn, meanq, rstdq, xin = ops.layernorm_fwd(xq_prev, W.qn_w, W.qn_b, add=pos, want_xsum=True)
+    kvn, meank, rstdk, _ = ops.layernorm_fwd(kv_in, W.kvn_w, W.kvn_b)
+    q = _empty((T, D), BF16, xq_prev)
+    ops.gemm(qn, W.wq, q)
+    kvp = _empty((Tk, 2 * D), BF16, xq_prev)
+    ops.gemm(kvn, W.wkv, kvp)
+    o, lse = ops.attention_fwd(q, kvp[:, :D], kvp[:, D:], B, H, L, Lk, cfg.scale, cfg.p_attn, seed, op_base)
+    x1 = _empty((T, D), F32, xq_prev)
+    ops.gemm(o, W.wo, x1, bias=W.bo, mode=EPI_RESIDUAL, resid=xin, drop_p=cfg.p_res1, seed=seed, op_id=op_base + 1)
+    x2, cm = _mlp_fwd(x1, W, T, D, cfg.p_res2, seed, op_base + 2, save)
+    ctx = NS(qn=qn, meanq=meanq, rstdq=rstdq, xin=xin, kvn=kvn, meank=meank, rstdk=rstdk, kv_in=kv_in, q=q, kvp=kvp,
+             o=o, lse=lse, mlp=cm) if save else None
+    return x2, ctx
+
+
+def ca_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, need_dkv=True):
+    B, L, Lk, D, H = cfg.B, cfg.L, cfg.Lk, cfg.D, cfg.H
+    T, Tk = B * L, B * Lk
+    dx1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2)
+    g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
+    _wgrad(g1, c.o, G.wo)
+    do = _empty((T, D), BF16, dx2)
+    _dgrad(g1, W.wo, do)
+    dq = _empty((T, D), BF16, dx2)
+    dkvp = _empty((Tk, 2 * D), BF16, dx2)
+    ops.attention_bwd(c.q, c.kvp[:, :D], c.kvp[:, D:], c.o, do, c.lse, dq, dkvp[:, :D], dkvp[:, D:], B, H, L, Lk,
+                      cfg.scale, cfg.p_attn, seed, op_base)
+    _wgrad(dq, c.qn, G.wq)
+    dqn = _empty((T, D), F32, dx2)
+    _dgrad(dq, W.wq, dqn)
+    dxq = ops.layernorm_bwd(dqn, c.xin, c.meanq, c.rstdq, W.qn_w, dres=dx1, dgamma=G.qn_w, dbeta=G.qn_b, dpos=dpos)
+    _wgrad(dkvp, c.kvn, G.wkv)
+    kv_bf16 = c.kv_in.dtype == BF16
+    dkvn = _empty((Tk, D), BF16 if kv_bf16 else F32, dx2)
+    _dgrad(dkvp, W.wkv, dkvn)
+    dkv = ops.layernorm_bwd(dkvn, c.kv_in, c.meank, c.rstdk, W.kvn_w, dgamma=G.kvn_w, dbeta=G.kvn_b,
+                            out_dtype=BF16 if kv_bf16 else F32)
+    return dxq, dkv
+
+
+# ==================================================================== Group2Emb (utils.py:144-189)
+def group2emb_fwd(nb, W, bn, cfg, training, save=True):
+    """nb fp32 [B,G,S,3] -> tokens fp32 [B*G, D].  bn holds the two BatchNorm1d running-stat pairs."""
+    Gt, S, D = cfg.Gt, cfg.S, cfg.D
+    R = Gt * S
+    assert S & (S - 1) == 0, "group_size must be a power of two (row-group bias epilogue)"
+    if training:
+        stats1 = ops.linear3_stats(nb, 3, W.w1, W.b1, R)
+    else:
+        stats1 = None
+    st1 = ops.bn_stats_finalize(stats1, R, W.bn1_w, W.bn1_b, bn.rm1, bn.rv1, training)
+    _, h1 = ops.linear3_fwd(nb, 3, W.w1, W.b1, R, scale=st1.scale, shift=st1.shift, act=ACT_RELU)
+    f2 = _empty((R, 128), BF16, nb)
+    ops.gemm(h1, W.w2, f2, bias=W.b2)
+    gmax, _, am2 = ops.group_max_fwd(f2, Gt, S, 128)
+    # conv3 on cat([global, local]) split into a per-group and a per-point half (saves 1/4 of the block's FLOPs)
+    u = _empty((Gt, 256), F32, nb)
+    ops.gemm(gmax, W.w3[:, :128], u, bias=W.b3)
+    y3 = _empty((R, 256), BF16, nb)
+    ops.gemm(f2, W.w3[:, 128:], y3, rg_bias=u, rg_shift=int(math.log2(S)))
+    h3, st3 = ops.bn_forward(y3, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, training, True)
+    y4 = _empty((R, D), BF16, nb)
+    ops.gemm(h3, W.w4, y4, bias=W.b4)
+    _, tok, am4 = ops.group_max_fwd(y4, Gt, S, D, want_bf16=False, want_f32=True)
+    ctx = NS(nb=nb, st1=st1, h1=h1, f2=f2, gmax=gmax, am2=am2, y3=y3, st3=st3, h3=h3, am4=am4) if save else None
+    return tok, ctx
+
+
+def group2emb_bwd(dtok, c, W, G, cfg):
+    Gt, S, D = cfg.Gt, cfg.S, cfg.D
+    R = Gt * S
+    ops.colsum(dtok, sum32=G.b4)
+    dy4 = ops.group_max_bwd(dtok, c.am4, Gt, S, D)
+    _wgrad(dy4, c.h3, G.w4)
+    dh3 = _empty((R, 256), BF16, dtok)
+    _dgrad(dy4, W.w4, dh3)
+    del dy4
+    dy3 = ops.bn_backward(dh3, c.y3, c.st3, True, G.bn3_w, G.bn3_b)
+    del dh3
+    _wgrad(dy3, c.f2, G.w3[:, 128:])
+    df2 = _empty((R, 128), BF16, dtok)
+    _dgrad(dy3, W.w3[:, 128:], df2)
+    dug, _ = ops.group_sum(dy3, Gt, S, 256)
+    del dy3
+    ops.colsum(dug, sum32=G.b3)
+    _wgrad(dug, c.gmax, G.w3[:, :128])
+    dgmax = _empty((Gt, 128), F32, dtok)
+    _dgrad(dug, W.w3[:, :128], dgmax)
+    ops.group_max_bwd(dgmax, c.am2, Gt, S, 128, dx=df2)
+    ops.colsum(df2, sum32=G.b2)
+    _wgrad(df2, c.h1, G.w2)
+    dh1 = _empty((R, 64), BF16, dtok)
+    _dgrad(df2, W.w2, dh1)
+    ops.linear3_bn_bwd(dh1, c.nb, 3, W.w1, W.b1, c.st1, G.w1, G.b1, G.bn1_w, G.bn1_b, R)
+
+
+# ====================================================== PointCloudInputAdapter (classifier.py:25-50)
+def adapter_fwd(pts, W, save=True):
+    """pts fp32 [B,N,C] -> bf16 [B*N, D]."""
+    B, N, C = pts.shape
+    R = B * N
+    y1, _ = ops.linear3_fwd(pts, C, W.w1, W.b1, R, want_pre=True)
+    h, mean, rstd, _ = ops.layernorm_fwd(y1, W.ln_w, W.ln_b, relu=True)
+    e = _empty((R, W.w2.shape[0]), BF16, pts)
+    ops.gemm(h, W.w2, e, bias=W.b2)
+    return e, (NS(pts=pts, y1=y1, h=h, mean=mean, rstd=rstd) if save else None)
+
+
+def adapter_bwd(de, c, W, G):
+    B, N, C = c.pts.shape
+    R = B * N
+    if de.dtype != BF16:
+        de = ops.dropout_grad(de, 0.0, None, 0)
+    ops.colsum(de, sum32=G.b2)
+    _wgrad(de, c.h, G.w2)
+    dh = _empty((R, 64), BF16, de)
+    _dgrad(de, W.w2, dh)
+    dy1 = ops.layernorm_bwd(dh, c.y1, c.mean, c.rstd, W.ln_w, y_relu=c.h, dgamma=G.ln_w, dbeta=G.ln_b, out_dtype=BF16)
+    ops.linear3_bwd(dy1, c.pts, C, G.w1, G.b1, R)
+
+
+# ============================================================== position_emb (partseg.py:498-501)
+def posemb_fwd(center, W, save=True):
+    """center fp32 [B,G,3] -> fp32 [B*G, D]."""
+    R = center.shape[0] * center.shape[1]
+    z, h = ops.linear3_fwd(center, center.shape[2], W.w1, W.b1, R, want_pre=True, act=ACT_GELU)
+    pos = _empty((R, W.w2.shape[0]), F32, center)
+    ops.gemm(h, W.w2, pos, bias=W.b2)
+    return pos, (NS(center=center, z=z, h=h) if save else None)
+
+
+def posemb_bwd(dpos, c, W, G):
+    R = c.z.shape[0]
+    g = ops.dropout_grad(dpos, 0.0, None, 0, colsum=G.b2)
+    _wgrad(g, c.h, G.w2)
+    dz = _empty((R, 128), BF16, dpos)
+    _dgrad(g, W.w2, dz, aux=c.z, aux_mode=AUX_GELU_GRAD)
+    ops.linear3_bwd(dz, c.center, c.center.shape[2], G.w1, G.b1, R)
+
+
+# ================================================================= patch2emb (partseg.py:631-634)
+def patch2emb_fwd(imgs, W, patch, save=True):
+    """imgs fp32 [B,H,W,3] NHWC -> fp32 [B*np, D]."""
+    P = ops.patchify(imgs, patch)
+    e = _empty((P.shape[0], W.w.shape[0]), F32, imgs)
+    ops.gemm(P, W.w, e, bias=W.b)
+    return e, (NS(P=P) if save else None)
+
+
+def patch2emb_bwd(de, c, G):
+    g = ops.dropout_grad(de, 0.0, None, 0, colsum=G.b)
+    _wgrad(g, c.P, G.w)
+
+
+# ===================================================== pooling + latent_head (partseg.py:519-525,547-548)
+def pool_head_fwd(x, W, bn, B, L, D, training, save=True):
+    """x fp32 [B*L, D] -> (feats fp32 [B, D], backbone fp32 [B, 2D])."""
+    pooled, am = ops.token_pool_fwd(x, B, L, D)
+    a1, st1 = ops.bn_forward(pooled, W.bn1_w, W.bn1_b, bn.rm1, bn.rv1, training, True)
+    y2 = _empty((B, D), F32, x)
+    ops.gemm(a1, W.wa, y2)
+    a2, st2 = ops.bn_forward(y2, W.bn2_w, W.bn2_b, bn.rm2, bn.rv2, training, True)
+    feats = _empty((B, D), F32, x)
+    ops.gemm(a2, W.wb, feats)
+    ctx = NS(pooled=pooled, am=am, a1=a1, st1=st1, y2=y2, a2=a2, st2=st2) if save else None
+    return feats, pooled, ctx
+
+
+def pool_head_bwd(dfeats, dbackbone, c, W, G, B, L, D):
+    if dfeats is not None:
+        g = ops.dropout_grad(dfeats, 0.0, None, 0)
+        _wgrad(g, c.a2, G.wb)
+        da2 = _empty((B, D), BF16, g)
+        _dgrad(g, W.wb, da2)
+        dy2 = ops.bn_backward(da2, c.y2, c.st2, True, G.bn2_w, G.bn2_b, out_dtype=BF16)
+        _wgrad(dy2, c.a1, G.wa)
+        da1 = _empty((B, 2 * D), BF16, g)
+        _dgrad(dy2, W.wa, da1)
+        dpooled = ops.bn_backward(da1, c.pooled, c.st1, True, G.bn1_w, G.bn1_b, out_dtype=F32)
+        if dbackbone is not None:
+            dpooled = ops.add_scale(dpooled, dbackbone.contiguous(), 1.0)
+    else:
+        dpooled = dbackbone.contiguous()
+    return ops.token_pool_bwd(dpooled, c.am, B, L, D)

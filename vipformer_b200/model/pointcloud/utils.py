@@ -113,3 +113,98 @@ def divide_patches(points, num_groups, group_size, *, start_idx=None, generator=
     if return_indices:
         return neighbors, centers, fi, ki
     return neighbors, centers
+
+
+# ======================================================================================= modules (utils.py:144-252)
+import torch.nn as nn  # noqa: E402
+from types import SimpleNamespace as _NS  # noqa: E402
+
+from ... import functional as _Fn  # noqa: E402
+from ... import params as _params  # noqa: E402
+from ... import runtime as _rt  # noqa: E402
+
+
+class Sequential(nn.Sequential):
+    """utils.py:245-252 (tuple-forwarding Sequential); kept for class-structure / state_dict parity."""
+
+    def forward(self, *x):
+        for module in self:
+            if type(x) == tuple:
+                x = module(*x)
+            else:
+                x = module(x)
+        return x
+
+
+class Group2Emb(nn.Module):
+    """utils.py:144-189: mini-PointNet patch embedding.  forward(point_groups [B,G,S,3]) -> [B,G,dim_model].
+
+    Conv1d/BatchNorm1d below are parameter containers only (state_dict keys `first_conv.{0,1,3}`,
+    `second_conv.{0,1,3}` as in the reference); the forward is the kernel sequence of functional.group2emb_fwd:
+    K=3 conv + BN + ReLU in one SIMT kernel, three tcgen05 GEMMs, train-mode BatchNorm with fp64 batch statistics.
+    """
+
+    def __init__(self, dim_model, point_channels=3):
+        super().__init__()
+        if point_channels != 3:
+            raise NotImplementedError("Group2Emb kernels are built for xyz input (point_channels == 3)")
+        self.dim_model = dim_model
+        self.point_channels = point_channels
+        self.first_conv = nn.Sequential(nn.Conv1d(point_channels, 64, 1), nn.BatchNorm1d(64), nn.ReLU(inplace=True),
+                                        nn.Conv1d(64, 128, 1))
+        self.second_conv = nn.Sequential(nn.Conv1d(256, 256, 1), nn.BatchNorm1d(256), nn.ReLU(inplace=True),
+                                         nn.Conv1d(256, self.dim_model, 1))
+
+    def _weights(self):
+        f, s = self.first_conv, self.second_conv
+        wb = _params.wb
+        return _NS(w1=f[0].weight.view(64, 3), b1=f[0].bias, bn1_w=f[1].weight, bn1_b=f[1].bias,
+                   w2=wb(f[3].weight).view(128, 64), b2=f[3].bias, w3=wb(s[0].weight).view(256, 256), b3=s[0].bias,
+                   bn3_w=s[1].weight, bn3_b=s[1].bias, w4=wb(s[3].weight).view(self.dim_model, 256), b4=s[3].bias)
+
+    def _grads(self):
+        f, s = self.first_conv, self.second_conv
+        return _NS(w1=f[0].weight.grad.view(64, 3), b1=f[0].bias.grad, bn1_w=f[1].weight.grad, bn1_b=f[1].bias.grad,
+                   w2=f[3].weight.grad.view(128, 64), b2=f[3].bias.grad, w3=s[0].weight.grad.view(256, 256),
+                   b3=s[0].bias.grad, bn3_w=s[1].weight.grad, bn3_b=s[1].bias.grad,
+                   w4=s[3].weight.grad.view(self.dim_model, 256), b4=s[3].bias.grad)
+
+    def forward(self, point_groups):
+        return _Group2EmbFn.apply(point_groups, _rt.anchor(self), self)
+
+
+class _Group2EmbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, nb, anchor, mod):
+        _lib.require_cuda(nb)
+        arena = _rt.root_prepare(mod, nb.device)
+        bs, g, n, ch = nb.shape
+        if ch != 3:
+            raise NotImplementedError("Group2Emb kernels are built for xyz input (point_channels == 3)")
+        nb = nb.float().contiguous()
+        f, s = mod.first_conv, mod.second_conv
+        bn = _NS(rm1=f[1].running_mean, rv1=f[1].running_var, rm3=s[1].running_mean, rv3=s[1].running_var)
+        cfg = _NS(Gt=bs * g, S=n, D=mod.dim_model)
+        W = mod._weights()
+        save = any(ctx.needs_input_grad)
+        tok, c = _Fn.group2emb_fwd(nb, W, bn, cfg, mod.training, save)
+        if mod.training:
+            _rt.bump(f[1]); _rt.bump(s[1])
+        if save:
+            ctx.c, ctx.mod, ctx.arena, ctx.cfg, ctx.W = c, mod, arena, cfg, W
+        return tok.view(bs, g, mod.dim_model)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        ctx.arena.ensure_grads()
+        _Fn.group2emb_bwd(_rt.as_f32_2d(dtok, dtok.shape[-1]), ctx.c, ctx.W, ctx.mod._grads(), ctx.cfg)
+        ctx.c = None
+        return None, None, None   # point_groups is data: no gradient flows to the tokenizer (divide_patches)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """utils.py:192-242 -- part-segmentation head; a later scope row, not built yet."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        raise NotImplementedError("PointNetFeaturePropagation (part segmentation) is not part of the pre-training hot path")

@@ -202,6 +202,13 @@ def group_max_bwd(dout, argmax, G, S, C, dx=None):
     return dx
 
 
+def group_sum(x, G, S, C, want_bf16=True, want_f32=False):
+    ob = torch.empty((G, C), dtype=BF16, device=x.device) if want_bf16 else None
+    of = torch.empty((G, C), dtype=F32, device=x.device) if want_f32 else None
+    _lib.call("vpf_group_sum", _p(x), _p(ob), _p(of), _i(G), _i(S), _i(C), _s())
+    return ob, of
+
+
 def token_pool_fwd(x, B, L, D):
     out = torch.empty((B, 2 * D), dtype=F32, device=x.device)
     am = torch.empty((B, D), dtype=torch.int32, device=x.device)
