@@ -130,6 +130,13 @@ typedef struct vpf_gemm_epilogue {
   const void *aux;        /* optional bf16 [M, ld_aux] */
   const float *resid;     /* VPF_EPI_RESIDUAL: fp32 [M, ldc] */
   const unsigned long long *seed_ptr; /* device pointer to the step's dropout seed */
+  /* fused group max (torch.max over the S points of a patch, utils.py:180,188) on the fp32 accumulators:
+   * rows are grouped S at a time; gm_out_*[(row / S) * gm_ld + col] = max, gm_argmax = first maximal row.
+   * `out` may be NULL when only the pooled result is wanted. */
+  int gm_S, gm_ld;
+  float *gm_out_f32;
+  void *gm_out_bf16;
+  unsigned char *gm_argmax;
 } vpf_gemm_epilogue;
 
 int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb,

@@ -100,8 +100,8 @@ def perturb_state_dict(sd, seed):
                 v = v + 0.02 * noise
         out[k] = v.clone()
     for k in list(out.keys()):   # cross_attn_1 / cross_attn_n alias ONE module (partseg.py:295-300): keep them equal
-        if ".cross_attn_n." in k:
-            out[k] = out[k.replace(".cross_attn_n.", ".cross_attn_1.")].clone()
+        if "cross_attn_n." in k:
+            out[k] = out[k.replace("cross_attn_n.", "cross_attn_1.")].clone()
     return out
 
 

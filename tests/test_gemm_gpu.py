@@ -127,3 +127,30 @@ def test_gemm_strided_views():
     v = qkv[:, 2 * D:]
     ops.gemm(v, W, out)
     _close(out, v.float() @ W.float().t(), False)
+
+
+@pytest.mark.parametrize("S", [8, 16, 32])
+@pytest.mark.parametrize("store", [True, False])
+def test_gemm_group_max_epilogue(S, store):
+    """Fused per-patch max (utils.py:180,188) on the fp32 accumulators; first maximal row wins."""
+    from vipformer_b200 import ops
+
+    G, N, K = 77, 256, 128
+    M = G * S
+    A, Bm = _mk((M, K), 12), _mk((N, K), 13)
+    bias = torch.randn(N, device="cuda")
+    acc = A.float() @ Bm.float().t() + bias
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16) if store else None
+    gm_f = torch.empty((G, N), device="cuda")
+    gm_b = torch.empty((G, N), device="cuda", dtype=torch.bfloat16)
+    am = torch.empty((G, N), device="cuda", dtype=torch.uint8)
+    ops.gemm(A, Bm, out, bias=bias, gm_S=S, gm_f32=gm_f, gm_bf16=gm_b, gm_argmax=am)
+    ref, ri = acc.view(G, S, N).max(1)
+    _close(gm_f, ref, False)
+    _close(gm_b, ref, True)
+    if store:
+        _close(out, acc, True)
+    # argmax must point at a row whose value equals the maximum up to accumulation-order noise
+    picked = acc.view(G, S, N).gather(1, am.long()[:, None]).squeeze(1)
+    assert (ref - picked).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert (am.long() == ri).float().mean().item() > 0.995

@@ -171,7 +171,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c, r);
         ptx::tmem_ld_wait();
         const int col0 = n_tile * BN + c;
-        if (!row_ok || col0 >= g.N) continue;
+        if (col0 >= g.N) continue;          // warp-uniform
+        if (!row_ok && e.gm_S == 0) continue; // per-lane (no warp collectives follow unless gm_S > 0)
         const int ncols = min(32, g.N - col0);
         float v[32];
 #pragma unroll
@@ -197,7 +198,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               *reinterpret_cast<uint4 *>(o2 + j) = pk;
             }
           } else {
-            for (int j = 0; j < ncols; ++j) o2[j] = __float2bfloat16(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) o2[j] = __float2bfloat16(v[j]);
           }
         }
         if (e.act == VPF_ACT_RELU) {
@@ -217,6 +219,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
+        if (e.gm_S > 0) {
+          // max over the gm_S rows of each group on the fp32 accumulators (torch.max over a patch's points,
+          // utils.py:180,188), first index wins; group leaders write max (+ argmax for the backward scatter)
+          const int S = e.gm_S, gbase = lane & ~(S - 1);
+          const unsigned gmask = (S == 32 ? 0xffffffffu : ((1u << S) - 1u) << gbase);
+          float mx[32];
+          uint32_t am_pack[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) am_pack[j] = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float m = v[j];
+            if (S == 32) {
+              uint32_t u = __float_as_uint(m);
+              u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+              u = __reduce_max_sync(0xffffffffu, u);
+              m = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+            } else {
+              for (int o = S >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, v[j] == m) & gmask;
+            const int am = bal ? (__ffs(bal) - 1 - gbase) : 0;
+            mx[j] = m;
+            am_pack[j >> 2] |= (uint32_t)am << ((j & 3) * 8);
+          }
+          if (lane == gbase && row_ok) {
+            const size_t go = (size_t)(grow / S) * e.gm_ld + col0;
+            if (ncols == 32) {
+              if (e.gm_out_f32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(e.gm_out_f32 + go + j) = make_float4(mx[j], mx[j + 1], mx[j + 2], mx[j + 3]);
+              }
+              if (e.gm_out_bf16) {
+                __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16) + go;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(mx[j + 2 * q], mx[j + 2 * q + 1]);
+                  *reinterpret_cast<uint4 *>(ob + j) = pk;
+                }
+              }
+              if (e.gm_argmax) {
+                uint4 *ap = reinterpret_cast<uint4 *>(e.gm_argmax + go);
+                ap[0] = make_uint4(am_pack[0], am_pack[1], am_pack[2], am_pack[3]);
+                ap[1] = make_uint4(am_pack[4], am_pack[5], am_pack[6], am_pack[7]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  if (e.gm_out_f32) e.gm_out_f32[go + j] = mx[j];
+                  if (e.gm_out_bf16) reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16)[go + j] = __float2bfloat16(mx[j]);
+                  if (e.gm_argmax) e.gm_argmax[go + j] = (uint8_t)((am_pack[j >> 2] >> ((j & 3) * 8)) & 0xff);
+                }
+              }
+            }
+          }
+          if (!e.out) continue;
+        }
         if (e.mode == VPF_EPI_STORE) {
           if (e.out_f32) {
             float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
@@ -224,7 +287,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
-              for (int j = 0; j < ncols; ++j) o[j] = v[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = v[j];
             }
           } else {
             __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(e.out) + (size_t)grow * e.ldc + col0;
@@ -238,7 +302,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 *reinterpret_cast<uint4 *>(o + j) = pk;
               }
             } else {
-              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16(v[j]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __float2bfloat16(v[j]);
             }
           }
         } else if (e.mode == VPF_EPI_RESIDUAL) {
@@ -263,7 +328,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j += 4) ptx::red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
-            for (int j = 0; j < ncols; ++j) atomicAdd(o + j, v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(o + j, v[j]);
           }
         }
       }
@@ -320,7 +386,8 @@ using namespace vpf;
 
 extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb, int M, int N, int K,
                              int splits, const vpf_gemm_epilogue *epi, void *stream) {
-  VPF_REQUIRE(A && B && epi && epi->out, "gemm: null pointer");
+  VPF_REQUIRE(A && B && epi && (epi->out || epi->gm_S > 0), "gemm: null pointer");
+  VPF_REQUIRE(epi->gm_S == 0 || ((epi->gm_S & (epi->gm_S - 1)) == 0 && epi->gm_S <= 32 && M % epi->gm_S == 0 && (epi->gm_ld % 16) == 0 && epi->mode == VPF_EPI_STORE), "gemm: group-max epilogue needs S a power of two <= 32 dividing M, gm_ld %% 16 == 0");
   VPF_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   VPF_REQUIRE(epi->mode == VPF_EPI_STORE || epi->mode == VPF_EPI_RESIDUAL || epi->mode == VPF_EPI_ATOMIC_ADD, "gemm: bad epilogue mode %d", epi->mode);
   VPF_REQUIRE(epi->mode != VPF_EPI_RESIDUAL || epi->resid, "gemm: residual epilogue needs resid");

@@ -148,18 +148,21 @@ def group2emb_fwd(nb, W, bn, cfg, training, save=True):
         stats1 = None
     st1 = ops.bn_stats_finalize(stats1, R, W.bn1_w, W.bn1_b, bn.rm1, bn.rv1, training)
     _, h1 = ops.linear3_fwd(nb, 3, W.w1, W.b1, R, scale=st1.scale, shift=st1.shift, act=ACT_RELU)
+    # conv2 with the per-patch max pooled from the fp32 accumulators in the GEMM epilogue (utils.py:180)
     f2 = _empty((R, 128), BF16, nb)
-    ops.gemm(h1, W.w2, f2, bias=W.b2)
-    gmax, _, am2 = ops.group_max_fwd(f2, Gt, S, 128)
+    gmax = _empty((Gt, 128), BF16, nb)
+    am2 = _empty((Gt, 128), torch.uint8, nb)
+    ops.gemm(h1, W.w2, f2, bias=W.b2, gm_S=S, gm_bf16=gmax, gm_argmax=am2)
     # conv3 on cat([global, local]) split into a per-group and a per-point half (saves 1/4 of the block's FLOPs)
     u = _empty((Gt, 256), F32, nb)
     ops.gemm(gmax, W.w3[:, :128], u, bias=W.b3)
     y3 = _empty((R, 256), BF16, nb)
     ops.gemm(f2, W.w3[:, 128:], y3, rg_bias=u, rg_shift=int(math.log2(S)))
     h3, st3 = ops.bn_forward(y3, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, training, True)
-    y4 = _empty((R, D), BF16, nb)
-    ops.gemm(h3, W.w4, y4, bias=W.b4)
-    _, tok, am4 = ops.group_max_fwd(y4, Gt, S, D, want_bf16=False, want_f32=True)
+    # conv4 + max over the patch (utils.py:188): pooled in the epilogue, the [R, D] pre-pool tensor is never stored
+    tok = _empty((Gt, D), F32, nb)
+    am4 = _empty((Gt, D), torch.uint8, nb)
+    ops.gemm(h3, W.w4, None, bias=W.b4, gm_S=S, gm_f32=tok, gm_argmax=am4)
     ctx = NS(nb=nb, st1=st1, h1=h1, f2=f2, gmax=gmax, am2=am2, y3=y3, st3=st3, h3=h3, am4=am4) if save else None
     return tok, ctx
 
