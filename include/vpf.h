@@ -213,8 +213,9 @@ int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float
                        const float *scale, const float *shift, const float *mean, const float *rstd,
                        double *red, float *dW, float *db, float *dgamma, float *dbeta, long long R,
                        int Co, void *stream);
-/* Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)', partseg.py:632 (fp32 NHWC -> bf16 rows). */
-int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, void *stream);
+/* Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)', partseg.py:632 (fp32 NHWC, or NCHW
+ * with nchw=1 which folds the permute of pretrain.py:179, -> bf16 rows). */
+int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, int nchw, void *stream);
 int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream);
 
 /* ------------------------------------------------------------------ loss + optimiser

@@ -204,9 +204,10 @@ __global__ void bn_param_grad_kernel(const double *__restrict__ red, float *__re
 }
 
 // ----------------------------------------------------------------- patchify
-// img fp32 [B,H,W,Ci] -> out bf16 [B*(H/P)*(W/P), P*P*Ci] in (p1 p2 c) order
+// img fp32 [B,H,W,Ci] (NHWC, what CrossFormer_img_mp.forward receives) or [B,Ci,H,W] (NCHW, what the data loader
+// yields before pretrain.py:179 permutes it) -> out bf16 [B*(H/P)*(W/P), P*P*Ci] in (p1 p2 c) order
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float *__restrict__ img, bf16 *__restrict__ out, int H, int W, int Ci, int P, size_t total) {
+patchify_kernel(const float *__restrict__ img, bf16 *__restrict__ out, int H, int W, int Ci, int P, int nchw, size_t total) {
   const int nw = W / P, nh = H / P, pd = P * P * Ci;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
     const int k = (int)(e % pd);
@@ -214,7 +215,9 @@ patchify_kernel(const float *__restrict__ img, bf16 *__restrict__ out, int H, in
     const int pw = (int)(row % nw), ph = (int)((row / nw) % nh);
     const size_t b = row / ((size_t)nw * nh);
     const int c = k % Ci, p2 = (k / Ci) % P, p1 = k / (Ci * P);
-    out[e] = __float2bfloat16(img[((b * H + (size_t)ph * P + p1) * W + (size_t)pw * P + p2) * Ci + c]);
+    const size_t y = (size_t)ph * P + p1, x = (size_t)pw * P + p2;
+    const size_t src = nchw ? ((b * Ci + c) * H + y) * W + x : ((b * H + y) * W + x) * Ci + c;
+    out[e] = __float2bfloat16(img[src]);
   }
 }
 
@@ -314,12 +317,12 @@ int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float
   return check_launch("bn_param_grad_kernel");
 }
 
-int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, void *stream) {
+int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, int nchw, void *stream) {
   VPF_REQUIRE(img && out_bf16, "patchify: null pointer");
   VPF_REQUIRE(P > 0 && H % P == 0 && W % P == 0, "patchify: image %dx%d not divisible by patch %d", H, W, P);
   const size_t total = (size_t)B * H * W * Ci;
   if (total == 0) return VPF_OK;
-  patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (bf16 *)out_bf16, H, W, Ci, P, total);
+  patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (bf16 *)out_bf16, H, W, Ci, P, nchw, total);
   return check_launch("patchify_kernel");
 }
 

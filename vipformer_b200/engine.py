@@ -1,0 +1,132 @@
+"""Data-parallel pre-training step: the hot loop of pretrain.py:173-211, one process per GPU.
+
+    for ((pc_t1, pc_t2), imgs) in loader:  forward both branches -> NT-Xent (intra + cross modal) -> backward
+                                           -> gradient all-reduce (DDP, pretrain.py:104-105) -> AdamW (:121-124,:210)
+
+B200-first structure:
+  * both models live in ONE parameter arena: a single flat fp32 gradient buffer is zeroed by one memset, all-reduced
+    by ONE NCCL call over NVLink/NVSwitch, and consumed by ONE fused AdamW kernel that also refreshes the bf16 shadows;
+  * the whole step (FPS start draw, ~600 kernel launches, collectives, optimizer) is captured in a CUDA graph and
+    replayed; per-step dropout seeds / step count / learning rate live in device memory so the graph stays valid;
+  * with world_size > 1 NT-Xent negatives span the global batch (all-gather of normalised embeddings + of the per-row
+    log-sum-exp); BatchNorm statistics stay rank-local exactly like the reference (no SyncBN);
+  * GradScaler (pretrain.py:154,209-211) is dropped: bf16 operands with fp32 accumulation need no loss scaling.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, params, runtime
+from .loss import pretrain_loss
+
+F32 = torch.float32
+
+
+class PretrainEngine:
+    def __init__(self, pc_model, img_model, *, batch_pairs, num_points, img_size=144, lr=1e-3, betas=(0.9, 0.999),
+                 eps=1e-8, weight_decay=1e-2, temperature=0.1, cmid_weight=1.0, gather_distributed=None,
+                 use_cuda_graph=True, seed=0, device=None, images_nchw=True):
+        import torch.distributed as dist
+
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.gather = (self.world > 1) if gather_distributed is None else bool(gather_distributed)
+        self.pc_model, self.img_model = pc_model.to(self.device).train(), img_model.to(self.device).train()
+        self.root = nn.ModuleList([self.pc_model, self.img_model])
+        for m in self.root.modules():
+            object.__setattr__(m, "_vpf_root", self.root) if m is not self.root else None
+        if self.dist:   # DDP wrap-time parameter broadcast (pretrain.py:104-105)
+            for p in self.root.parameters():
+                self.dist.broadcast(p.data, src=0)
+            for b in self.root.buffers():
+                self.dist.broadcast(b.data, src=0)
+        self.arena = params.prepare(self.root, self.device)
+        self.arena.ensure_grads()
+        self.arena.refresh_shadows(force=True)
+        self.arena.managed = True
+        n = self.arena.flat_p.numel()
+        self.m = ops.zeros_(torch.empty(n, dtype=F32, device=self.device))
+        self.v = ops.zeros_(torch.empty(n, dtype=F32, device=self.device))
+        self.lr = torch.tensor([lr], dtype=F32, device=self.device)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.temperature, self.cmid_weight = temperature, cmid_weight
+        self.state = runtime.StepState.get(self.device)
+        runtime.manual_seed(seed * 1000003 + self.rank, self.device)
+        b = batch_pairs
+        self.b, self.N = b, num_points
+        self.images_nchw = images_nchw
+        # static step inputs (graph-stable addresses); [t1; t2] is the concatenation of pretrain.py:183
+        self.pc_in = torch.zeros((2 * b, num_points, 3), dtype=F32, device=self.device)
+        ishape = (b, 3, img_size, img_size) if images_nchw else (b, img_size, img_size, 3)
+        self.img_in = torch.zeros(ishape, dtype=F32, device=self.device)
+        self.start = torch.zeros(2 * b, dtype=torch.long, device=self.device)
+        self.losses = torch.zeros(3, dtype=F32, device=self.device)
+        self.losses_host = torch.zeros(3, dtype=F32).pin_memory()
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(1234 + self.rank)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------------------------------------ one step
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def _step_body(self):
+        ops.step_advance(self.state)                      # step += 1, fresh dropout seed
+        self.arena.zero_grads()                           # optimizer.zero_grad (pretrain.py:174)
+        torch.randint(0, self.N, (2 * self.b,), dtype=torch.long, device=self.device, generator=self.gen, out=self.start)
+        self.pc_model.fps_start_idx = self.start          # utils.py:71, drawn on the device
+        pc_feats, _ = self.pc_model(self.pc_in)           # pretrain.py:186
+        imgs = self.img_in.permute(0, 2, 3, 1) if self.images_nchw else self.img_in   # pretrain.py:179
+        img_feats, _ = self.img_model(imgs)               # pretrain.py:199
+        losses = pretrain_loss(pc_feats, img_feats, self.temperature, self.cmid_weight, self.gather)
+        losses[0].backward()                              # pretrain.py:209
+        if self.dist:                                     # DDP gradient all-reduce (mean), one flat buffer
+            self.dist.all_reduce(self.arena.flat_g, op=self.dist.ReduceOp.AVG)
+        ops.adamw(self.arena.flat_p, self.arena.flat_g, self.m, self.v, self.arena.flat_bf, self.lr, self.state[:1],
+                  self.betas[0], self.betas[1], self.eps, self.weight_decay)   # pretrain.py:210
+        ops.add_scale(losses.detach(), None, 1.0, out=self.losses)
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                            # warm-up outside capture (allocator, lazy init, NCCL)
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.gen_state_registered = False
+        try:
+            self.graph.register_generator_state(self.gen)
+        except Exception:
+            pass
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        self.steps_done += 2
+
+    def step(self):
+        """Run one optimisation step on whatever is in self.pc_in / self.img_in; returns the device tensor
+        (total, loss_imid, loss_cmid) without synchronising."""
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.steps_done += 1
+        return self.losses
+
+    def step_host(self, pc_t1, pc_t2, imgs):
+        """End-to-end step from (pinned) HOST tensors: H2D copies, the step, D2H read of the losses (synchronises).
+        pc_t1/pc_t2 [b,N,3] fp32, imgs [b,3,H,W] fp32 (what the reference's DataLoader yields, pretrain.py:173-179)."""
+        b = self.b
+        self.pc_in[:b].copy_(pc_t1, non_blocking=True)
+        self.pc_in[b:].copy_(pc_t2, non_blocking=True)
+        self.img_in.copy_(imgs, non_blocking=True)
+        self.step()
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.losses_host

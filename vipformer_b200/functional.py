@@ -240,9 +240,9 @@ def posemb_bwd(dpos, c, W, G):
 
 
 # ================================================================= patch2emb (partseg.py:631-634)
-def patch2emb_fwd(imgs, W, patch, save=True):
-    """imgs fp32 [B,H,W,3] NHWC -> fp32 [B*np, D]."""
-    P = ops.patchify(imgs, patch)
+def patch2emb_fwd(imgs, W, patch, save=True, nchw=False):
+    """imgs fp32 [B,H,W,3] NHWC (or [B,3,H,W] with nchw) -> fp32 [B*np, D]."""
+    P = ops.patchify(imgs, patch, nchw)
     e = _empty((P.shape[0], W.w.shape[0]), F32, imgs)
     ops.gemm(P, W.w, e, bias=W.b)
     return e, (NS(P=P) if save else None)

@@ -385,10 +385,12 @@ class _Patch2EmbFn(torch.autograd.Function):
     def forward(ctx, imgs, anchor, mod):
         _lib.require_cuda(imgs)
         arena = _root_prepare(mod, imgs.device)
-        imgs = imgs.float().contiguous()
+        # a permuted NCHW view (pretrain.py:179 `torch.permute(imgs, (0, 2, 3, 1))`) is consumed in place
+        nchw = (not imgs.is_contiguous()) and imgs.permute(0, 3, 1, 2).is_contiguous()
+        imgs = imgs.float() if nchw else imgs.float().contiguous()
         W = NS(w=params.wb(mod[1].weight), b=mod[1].bias)
         save = any(ctx.needs_input_grad)
-        e, c = Fn.patch2emb_fwd(imgs, W, mod.patch_size, save)
+        e, c = Fn.patch2emb_fwd(imgs.permute(0, 3, 1, 2) if nchw else imgs, W, mod.patch_size, save, nchw)
         if save:
             ctx.c, ctx.mod, ctx.arena = c, mod, arena
         return e.view(imgs.shape[0], -1, e.shape[-1])
@@ -476,7 +478,8 @@ class CrossFormer_pc_mp(nn.Module):
         self.fps_generator = None
 
     def _tokens(self, pts):
-        _set_root(self)
+        if self.__dict__.get("_vpf_root") is None:
+            _set_root(self)
         pts = pts.float().contiguous()
         pts_embs = self.input_adapter(pts)
         neighborhood, center = divide_patches(pts, self.num_groups, self.group_size, start_idx=self.fps_start_idx,
@@ -514,7 +517,8 @@ class CrossFormer_img_mp(nn.Module):
         self.latent_head = _latent_head(num_latent_channels)
 
     def forward(self, imgs):
-        _set_root(self)
+        if self.__dict__.get("_vpf_root") is None:
+            _set_root(self)
         patch_embs = self.patch2emb(imgs)
         pos_embs = self.position_emb
         x_latent = self.encoder(patch_embs, pos_embs, patch_embs)

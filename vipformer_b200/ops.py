@@ -255,10 +255,13 @@ def linear3_bn_bwd(dh, p, ldp, w, b, st, dW, db, dgamma, dbeta, R):
               _p(st.rstd), _p(red), _p(dW), _p(db), _p(dgamma), _p(dbeta), _ll(R), _i(Co), _s())
 
 
-def patchify(img, P):
-    B, H, W, Ci = img.shape
+def patchify(img, P, nchw=False):
+    if nchw:
+        B, Ci, H, W = img.shape
+    else:
+        B, H, W, Ci = img.shape
     out = torch.empty((B * (H // P) * (W // P), P * P * Ci), dtype=BF16, device=img.device)
-    _lib.call("vpf_patchify", _p(img), _p(out), _i(B), _i(H), _i(W), _i(Ci), _i(P), _s())
+    _lib.call("vpf_patchify", _p(img), _p(out), _i(B), _i(H), _i(W), _i(Ci), _i(P), _i(int(nchw)), _s())
     return out
 
 
