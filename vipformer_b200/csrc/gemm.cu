@@ -7,7 +7,7 @@
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128 N=128 K=16; accumulators in TMEM,
 //                               two 128-column accumulator stages so the epilogue of tile i
 //                               overlaps the main loop of tile i+1)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> smem transpose -> fused epilogue -> coalesced global)
 //
 // Both operands may be K-major (row-major [rows][K]) or MN-major ([K][rows]); that covers the
 // forward (X.W^T), the data gradient (dY.W) and the weight gradient (dY^T.X, split-K with
@@ -25,7 +25,8 @@ constexpr int kStages = 6;
 constexpr int kTileBytesA = BM * BK * 2, kTileBytesB = BN * BK * 2;
 constexpr int kStageBytes = kTileBytesA + kTileBytesB;
 constexpr int kGemmThreads = 192;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStgLd = 36;   // padded row stride (floats) of the per-warp epilogue transpose tile
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4 /*epilogue staging*/;
 constexpr int kTmemCols = 2 * BN;
 
 struct GemmArgs {
@@ -144,17 +145,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    // TMEM gives each lane one ROW (32 fp32 columns per tcgen05.ld).  Global traffic wants lanes along a row,
+    // so every 32x32 chunk is transposed through a padded per-warp shared-memory tile: afterwards 8 lanes cover
+    // 128 contiguous bytes of one output row and a warp instruction touches 4 rows -> fully coalesced float4 /
+    // bf16x4 loads (bias, residual, aux) and stores.  The per-patch max pool reads the same tile column-wise.
     const vpf_gemm_epilogue &e = g.e;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int row_in_tile = quad * 32 + lane;
-    uint32_t drop_thr = 0;
-    uint32_t drop_key = 0;
+    float *stg = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256) + (warp - 2) * (32 * kStgLd);
+    uint32_t drop_thr = 0, drop_key = 0;
     float drop_scale = 1.f;
     if (e.mode == VPF_EPI_RESIDUAL && e.drop_p > 0.f) {
       drop_thr = rng::threshold(e.drop_p);
       drop_key = rng::make_key(e.seed_ptr ? *e.seed_ptr : 0ull, e.op_id);
       drop_scale = 1.f / (1.f - e.drop_p);
     }
+    const int cq = (lane & 7) * 4, rsub = lane >> 3;
+    const bool vec_ok = (e.ldc & 3) == 0;
     int iter = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++iter) {
       const int n_tile = w % g.num_n_tiles;
@@ -162,8 +168,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int acc = iter & 1;
       ptx::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
       ptx::tc_fence_after();
-      const long long grow = (long long)m_tile * BM + row_in_tile;
-      const bool row_ok = grow < g.M;
+      const long long row0 = (long long)m_tile * BM + quad * 32;   // first row of this warp's 32-row slab
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
@@ -171,165 +176,150 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c, r);
         ptx::tmem_ld_wait();
         const int col0 = n_tile * BN + c;
-        if (col0 >= g.N) continue;          // warp-uniform
-        if (!row_ok && e.gm_S == 0) continue; // per-lane (no warp collectives follow unless gm_S > 0)
-        const int ncols = min(32, g.N - col0);
-        float v[32];
+        if (col0 >= g.N || row0 >= g.M) continue;   // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
-        if (e.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(e.bias + col0 + j);
-        }
-        if (e.rg_bias) {
-          const float *rb = e.rg_bias + (size_t)(grow >> e.rg_shift) * e.rg_ld + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(rb + j);
-        }
-        if (e.out2) {  // pre-activation copy (bf16) for the backward pass
-          __nv_bfloat16 *o2 = reinterpret_cast<__nv_bfloat16 *>(e.out2) + (size_t)grow * e.ldc + col0;
-          if (ncols == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-              *reinterpret_cast<uint4 *>(o2 + j) = pk;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) o2[j] = __float2bfloat16(v[j]);
-          }
-        }
-        if (e.act == VPF_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (e.act == VPF_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
-        }
-        if (e.aux_mode != VPF_AUX_NONE) {
-          const __nv_bfloat16 *ax = reinterpret_cast<const __nv_bfloat16 *>(e.aux) + (size_t)grow * e.ld_aux + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-              const float a = __bfloat162float(ax[j]);
-              v[j] = e.aux_mode == VPF_AUX_GELU_GRAD ? v[j] * gelu_grad_f(a) : (a > 0.f ? v[j] : 0.f);
-            }
-          }
-        }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(stg + lane * kStgLd + j) =
+              make_float4(__uint_as_float(r[j]) * e.alpha, __uint_as_float(r[j + 1]) * e.alpha,
+                          __uint_as_float(r[j + 2]) * e.alpha, __uint_as_float(r[j + 3]) * e.alpha);
+        __syncwarp();
+
         if (e.gm_S > 0) {
-          // max over the gm_S rows of each group on the fp32 accumulators (torch.max over a patch's points,
-          // utils.py:180,188), first index wins; group leaders write max (+ argmax for the backward scatter)
-          const int S = e.gm_S, gbase = lane & ~(S - 1);
-          const unsigned gmask = (S == 32 ? 0xffffffffu : ((1u << S) - 1u) << gbase);
-          float mx[32];
-          uint32_t am_pack[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) am_pack[j] = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float m = v[j];
-            if (S == 32) {
-              uint32_t u = __float_as_uint(m);
-              u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-              u = __reduce_max_sync(0xffffffffu, u);
-              m = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-            } else {
-              for (int o = S >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, v[j] == m) & gmask;
-            const int am = bal ? (__ffs(bal) - 1 - gbase) : 0;
-            mx[j] = m;
-            am_pack[j >> 2] |= (uint32_t)am << ((j & 3) * 8);
-          }
-          if (lane == gbase && row_ok) {
-            const size_t go = (size_t)(grow / S) * e.gm_ld + col0;
-            if (ncols == 32) {
-              if (e.gm_out_f32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(e.gm_out_f32 + go + j) = make_float4(mx[j], mx[j + 1], mx[j + 2], mx[j + 3]);
+          // max over the gm_S rows of each patch on the fp32 accumulators (torch.max, utils.py:180,188), first
+          // index wins; lane = column.  Biases are constant down a column, so they are added after the max.
+          const int S = e.gm_S;
+          const int col = col0 + lane;
+          if (col < g.N) {
+            const float badd = e.bias ? __ldg(e.bias + col) : 0.f;
+            for (int gr = 0; gr < 32; gr += S) {
+              if (row0 + gr >= g.M) break;
+              float m = stg[gr * kStgLd + lane];
+              int am = 0;
+              for (int s2 = 1; s2 < S; ++s2) {
+                const float x = stg[(gr + s2) * kStgLd + lane];
+                if (x > m) { m = x; am = s2; }
               }
-              if (e.gm_out_bf16) {
-                __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16) + go;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk;
-                  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(mx[j + 2 * q], mx[j + 2 * q + 1]);
-                  *reinterpret_cast<uint4 *>(ob + j) = pk;
-                }
-              }
-              if (e.gm_argmax) {
-                uint4 *ap = reinterpret_cast<uint4 *>(e.gm_argmax + go);
-                ap[0] = make_uint4(am_pack[0], am_pack[1], am_pack[2], am_pack[3]);
-                ap[1] = make_uint4(am_pack[4], am_pack[5], am_pack[6], am_pack[7]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < ncols) {
-                  if (e.gm_out_f32) e.gm_out_f32[go + j] = mx[j];
-                  if (e.gm_out_bf16) reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16)[go + j] = __float2bfloat16(mx[j]);
-                  if (e.gm_argmax) e.gm_argmax[go + j] = (uint8_t)((am_pack[j >> 2] >> ((j & 3) * 8)) & 0xff);
-                }
-              }
+              m += badd;
+              const size_t go = (size_t)((row0 + gr) / S) * e.gm_ld + col;
+              if (e.gm_out_f32) e.gm_out_f32[go] = m;
+              if (e.gm_out_bf16) reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16)[go] = __float2bfloat16(m);
+              if (e.gm_argmax) e.gm_argmax[go] = (uint8_t)am;
             }
           }
           if (!e.out) continue;
         }
-        if (e.mode == VPF_EPI_STORE) {
-          if (e.out_f32) {
-            float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
-            if (ncols == 32) {
+
+        const int col = col0 + cq;
+        if (col >= g.N) continue;
+        const int nv = min(4, g.N - col);
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (e.bias) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int q = 0; q < 4; ++q) if (q < nv) b4[q] = __ldg(e.bias + col + q);
+        }
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + rsub;
+          const long long grow = row0 + rl;
+          if (grow >= g.M) continue;
+          const float4 t = *reinterpret_cast<const float4 *>(stg + rl * kStgLd + cq);
+          float v[4] = {t.x + b4[0], t.y + b4[1], t.z + b4[2], t.w + b4[3]};
+          const bool full = vec_ok && nv == 4;
+          if (e.rg_bias) {
+            const float *rb = e.rg_bias + (size_t)(grow >> e.rg_shift) * e.rg_ld + col;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < nv) v[q] += __ldg(rb + q);
+          }
+          const size_t off = (size_t)grow * e.ldc + col;
+          if (e.out2) {
+            __nv_bfloat16 *o2 = reinterpret_cast<__nv_bfloat16 *>(e.out2) + off;
+            if (full) {
+              uint2 pk;
+              *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+              *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+              *reinterpret_cast<uint2 *>(o2) = pk;
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = v[j];
+              for (int q = 0; q < 4; ++q) if (q < nv) o2[q] = __float2bfloat16(v[q]);
             }
-          } else {
-            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(e.out) + (size_t)grow * e.ldc + col0;
-            if (ncols == 32) {
+          }
+          if (e.act == VPF_ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+            for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
+          } else if (e.act == VPF_ACT_GELU) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-                *reinterpret_cast<uint4 *>(o + j) = pk;
+            for (int q = 0; q < 4; ++q) v[q] = gelu_f(v[q]);
+          }
+          if (e.aux_mode != VPF_AUX_NONE) {
+            const __nv_bfloat16 *ax = reinterpret_cast<const __nv_bfloat16 *>(e.aux) + (size_t)grow * e.ld_aux + col;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nv == 4 && (e.ld_aux & 3) == 0) {
+              const uint2 pk = *reinterpret_cast<const uint2 *>(ax);
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.x));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.y));
+              a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (q < nv) a[q] = __bfloat162float(ax[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              v[q] = e.aux_mode == VPF_AUX_GELU_GRAD ? v[q] * gelu_grad_f(a[q]) : (a[q] > 0.f ? v[q] : 0.f);
+          }
+          if (e.mode == VPF_EPI_STORE) {
+            if (e.out_f32) {
+              float *o = reinterpret_cast<float *>(e.out) + off;
+              if (full) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q < nv) o[q] = v[q];
               }
             } else {
+              __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(e.out) + off;
+              if (full) {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2 *>(o) = pk;
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __float2bfloat16(v[j]);
+                for (int q = 0; q < 4; ++q) if (q < nv) o[q] = __float2bfloat16(v[q]);
+              }
             }
-          }
-        } else if (e.mode == VPF_EPI_RESIDUAL) {
-          // out_f32 = resid + dropout(v)     (partseg.py:208-213 Residual)
-          const float *rs = e.resid + (size_t)grow * e.ldc + col0;
-          float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
-          __nv_bfloat16 *ob = e.out_bf16 ? reinterpret_cast<__nv_bfloat16 *>(e.out_bf16) + (size_t)grow * e.ldc + col0 : nullptr;
-          const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col0);
+          } else if (e.mode == VPF_EPI_RESIDUAL) {
+            // out_f32 = resid + dropout(v)     (partseg.py:208-213 Residual)
+            const float *rs = e.resid + off;
+            float *o = reinterpret_cast<float *>(e.out) + off;
+            float rv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full) { const float4 q4 = *reinterpret_cast<const float4 *>(rs); rv[0] = q4.x; rv[1] = q4.y; rv[2] = q4.z; rv[3] = q4.w; }
+            else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-              float y = v[j];
-              if (drop_thr) y = rng::keep(drop_key, ebase + j, drop_thr) ? y * drop_scale : 0.f;
-              const float s = rs[j] + y;
-              o[j] = s;
-              if (ob) ob[j] = __float2bfloat16(s);
+              for (int q = 0; q < 4; ++q) if (q < nv) rv[q] = rs[q];
             }
-          }
-        } else {  // VPF_EPI_ATOMIC_ADD: split-K weight gradients accumulate into the flat fp32 grad buffer
-          float *o = reinterpret_cast<float *>(e.out) + (size_t)grow * e.ldc + col0;
-          if (ncols == 32 && (e.ldc & 3) == 0) {
+            if (drop_thr) {
+              const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) ptx::red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+              for (int q = 0; q < 4; ++q) v[q] = rng::keep(drop_key, ebase + q, drop_thr) ? v[q] * drop_scale : 0.f;
+            }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(o + j, v[j]);
+            for (int q = 0; q < 4; ++q) v[q] += rv[q];
+            if (full) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (q < nv) o[q] = v[q];
+            }
+            if (e.out_bf16) {
+              __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(e.out_bf16) + off;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (q < nv) ob[q] = __float2bfloat16(v[q]);
+            }
+          } else {  // VPF_EPI_ATOMIC_ADD: split-K weight gradients accumulate into the flat fp32 grad buffer
+            float *o = reinterpret_cast<float *>(e.out) + off;
+            if (full) ptx::red_add_v4(o, v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (q < nv) atomicAdd(o + q, v[q]);
+            }
           }
         }
       }

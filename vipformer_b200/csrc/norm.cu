@@ -145,22 +145,35 @@ dropout_grad_kernel(const float *__restrict__ g, __nv_bfloat16 *__restrict__ out
 }
 
 // ------------------------------------------------------ column sum / sumsq
+// thread (tx, ty): tx owns a PAIR of adjacent columns (a warp row-read is 128/256 contiguous bytes), ty strides rows
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float *p, size_t i) { return *reinterpret_cast<const float2 *>(p + i); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16 *p, size_t i) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + i)); }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T *__restrict__ x, double *__restrict__ sum, double *__restrict__ sumsq, float *__restrict__ sum_f32,
-              long long R, int C, int rows_per_cta) {
+              long long R, int C, int rows_per_cta, int lanes_x) {
+  const int tx = threadIdx.x % lanes_x, ty = threadIdx.x / lanes_x, ny = 256 / lanes_x;
   const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  for (int c = threadIdx.x + blockIdx.y * 256; c < C; c += 256 * gridDim.y) {
-    double a = 0.0, q = 0.0;
-    for (long long r0 = row0; r0 < row1; r0 += 64) {
-      float pa = 0.f, pq = 0.f;
-      const long long r1 = min(row1, r0 + 64);
-      for (long long r = r0; r < r1; ++r) { const float v = ldf<T>(x, (size_t)r * C + c); pa += v; pq += v * v; }
-      a += pa; q += pq;
+  for (int cp = tx + blockIdx.y * lanes_x; cp < C / 2; cp += lanes_x * gridDim.y) {
+    double a0 = 0.0, a1 = 0.0, q0 = 0.0, q1 = 0.0;
+    for (long long r0 = row0 + ty; r0 < row1; r0 += (long long)ny * 32) {
+      float pa0 = 0.f, pa1 = 0.f, pq0 = 0.f, pq1 = 0.f;
+      const long long r1 = min(row1, r0 + (long long)ny * 32);
+      for (long long r = r0; r < r1; r += ny) {
+        const float2 v = Pair<T>::ld(x, (size_t)r * C + 2 * cp);
+        pa0 += v.x; pa1 += v.y; pq0 += v.x * v.x; pq1 += v.y * v.y;
+      }
+      a0 += pa0; a1 += pa1; q0 += pq0; q1 += pq1;
     }
-    if (sum) atomicAdd(sum + c, a);
-    if (sumsq) atomicAdd(sumsq + c, q);
-    if (sum_f32) atomicAdd(sum_f32 + c, (float)a);
+    if (sum) { atomicAdd(sum + 2 * cp, a0); atomicAdd(sum + 2 * cp + 1, a1); }
+    if (sumsq) { atomicAdd(sumsq + 2 * cp, q0); atomicAdd(sumsq + 2 * cp + 1, q1); }
+    if (sum_f32) { atomicAdd(sum_f32 + 2 * cp, (float)a0); atomicAdd(sum_f32 + 2 * cp + 1, (float)a1); }
   }
 }
 
@@ -214,25 +227,31 @@ template <typename Tdy, typename Tx>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
-                     int relu, double *__restrict__ red, long long R, int C, int rows_per_cta) {
+                     int relu, double *__restrict__ red, long long R, int C, int rows_per_cta, int lanes_x) {
+  const int tx = threadIdx.x % lanes_x, ty = threadIdx.x / lanes_x, ny = 256 / lanes_x;
   const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  for (int c = threadIdx.x + blockIdx.y * 256; c < C; c += 256 * gridDim.y) {
-    const float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
-    double a = 0.0, q = 0.0;
-    for (long long r0 = row0; r0 < row1; r0 += 64) {
-      float pa = 0.f, pq = 0.f;
-      const long long r1 = min(row1, r0 + 64);
-      for (long long r = r0; r < r1; ++r) {
-        const float xv = ldf<Tx>(x, (size_t)r * C + c);
-        float d = ldf<Tdy>(dy, (size_t)r * C + c);
-        if (relu && !(xv * sc + sh > 0.f)) d = 0.f;
-        pa += d;
-        pq += d * (xv - mu) * rs;
+  for (int cp = tx + blockIdx.y * lanes_x; cp < C / 2; cp += lanes_x * gridDim.y) {
+    const int c = 2 * cp;
+    const float sc0 = scale[c], sh0 = shift[c], mu0 = mean[c], rs0 = rstd[c];
+    const float sc1 = scale[c + 1], sh1 = shift[c + 1], mu1 = mean[c + 1], rs1 = rstd[c + 1];
+    double a0 = 0.0, a1 = 0.0, q0 = 0.0, q1 = 0.0;
+    for (long long r0 = row0 + ty; r0 < row1; r0 += (long long)ny * 32) {
+      float pa0 = 0.f, pa1 = 0.f, pq0 = 0.f, pq1 = 0.f;
+      const long long r1 = min(row1, r0 + (long long)ny * 32);
+      for (long long r = r0; r < r1; r += ny) {
+        const float2 xv = Pair<Tx>::ld(x, (size_t)r * C + c);
+        float2 d = Pair<Tdy>::ld(dy, (size_t)r * C + c);
+        if (relu) {
+          if (!(xv.x * sc0 + sh0 > 0.f)) d.x = 0.f;
+          if (!(xv.y * sc1 + sh1 > 0.f)) d.y = 0.f;
+        }
+        pa0 += d.x; pa1 += d.y;
+        pq0 += d.x * (xv.x - mu0) * rs0; pq1 += d.y * (xv.y - mu1) * rs1;
       }
-      a += pa; q += pq;
+      a0 += pa0; a1 += pa1; q0 += pq0; q1 += pq1;
     }
-    atomicAdd(red + c, a);
-    atomicAdd(red + C + c, q);
+    atomicAdd(red + c, a0); atomicAdd(red + c + 1, a1);
+    atomicAdd(red + C + c, q0); atomicAdd(red + C + c + 1, q1);
   }
 }
 
@@ -260,6 +279,63 @@ bn_bwd_apply_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const 
       dgamma[c] += (float)red[C + c];
       dbeta[c] += (float)red[c];
     }
+  }
+}
+
+// 8-wide bf16 fast paths (C % 8 == 0): one 16-byte load/store per tensor per thread
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+  return u;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_bf16x8_kernel(const uint4 *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
+                       uint4 *__restrict__ y, int relu, size_t total8, int C) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total8; i += (size_t)gridDim.x * 256) {
+    const int c = (int)((i * 8) % C);
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      f[q] = f[q] * scale[c + q] + shift[c + q];
+      if (relu) f[q] = fmaxf(f[q], 0.f);
+    }
+    y[i] = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_bf16x8_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const float *__restrict__ scale,
+                           const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                           int relu, const double *__restrict__ red, uint4 *__restrict__ dx, float *__restrict__ dgamma,
+                           float *__restrict__ dbeta, long long R, int C) {
+  const size_t total8 = (size_t)R * C / 8;
+  const float invR = (float)(1.0 / (double)R);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total8; i += (size_t)gridDim.x * 256) {
+    const int c = (int)((i * 8) % C);
+    float d[8], xv[8];
+    unpack8(dy[i], d);
+    unpack8(x[i], xv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float sc = scale[c + q];
+      float dd = d[q];
+      if (relu && !(xv[q] * sc + shift[c + q] > 0.f)) dd = 0.f;
+      const float xh = (xv[q] - mean[c + q]) * rstd[c + q];
+      d[q] = sc * (dd - (float)red[c + q] * invR - xh * (float)red[C + c + q] * invR);
+    }
+    dx[i] = pack8(d);
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += 256) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
   }
 }
 
@@ -336,14 +412,24 @@ int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p, con
   return check_launch("dropout_grad_kernel");
 }
 
+static inline void col_launch_cfg(long long R, int C, int &lanes_x, dim3 &grid, int &rows_per_cta) {
+  const int cpairs = C / 2;
+  lanes_x = 1;
+  while (lanes_x * 2 <= min(cpairs, 256)) lanes_x *= 2;            // power of two <= min(C/2, 256)
+  const int gy = ceil_div(cpairs, lanes_x);
+  rows_per_cta = (int)max((long long)(256 / lanes_x) * 32, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
+  grid = dim3((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
+}
+
 int vpf_colsum(const void *x, int x_bf16, double *sum, double *sumsq, float *sum_f32, long long R, int C, void *stream) {
   VPF_REQUIRE(x && (sum || sumsq || sum_f32), "colsum: null pointer");
+  VPF_REQUIRE(C % 2 == 0, "colsum: C=%d must be even", C);
   if (R == 0 || C == 0) return VPF_OK;
-  const int gy = ceil_div(C, 256);
-  const int rows_per_cta = (int)max((long long)64, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
-  dim3 grid((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
-  if (x_bf16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, sum, sumsq, sum_f32, R, C, rows_per_cta);
-  else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)x, sum, sumsq, sum_f32, R, C, rows_per_cta);
+  int lanes_x, rows_per_cta;
+  dim3 grid;
+  col_launch_cfg(R, C, lanes_x, grid, rows_per_cta);
+  if (x_bf16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, sum, sumsq, sum_f32, R, C, rows_per_cta, lanes_x);
+  else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)x, sum, sumsq, sum_f32, R, C, rows_per_cta, lanes_x);
   return check_launch("colsum_kernel");
 }
 
@@ -363,7 +449,8 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
   if (total == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(total);
-  if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
+  if (x_bf16 && y_bf16 && C % 8 == 0) bn_apply_bf16x8_kernel<<<grid_for(total / 8), 256, 0, st>>>((const uint4 *)x, scale, shift, (uint4 *)y, relu, total / 8, C);
+  else if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && y_bf16) bn_apply_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && !y_bf16) bn_apply_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (float *)y, relu, total, C);
   else return fail(VPF_EINVAL, "bn_apply: bf16 -> fp32 unsupported");
@@ -377,16 +464,22 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
   if (R == 0 || C == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   VPF_CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
-  const int gy = ceil_div(C, 256);
-  const int rows_per_cta = (int)max((long long)64, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
-  dim3 grid((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
+  VPF_REQUIRE(C % 2 == 0, "bn_bwd: C=%d must be even", C);
+  int lanes_x, rows_per_cta;
+  dim3 grid;
+  col_launch_cfg(R, C, lanes_x, grid, rows_per_cta);
   const int g2 = grid_for((size_t)R * C);
 #define BNB(TDY, TX, TDX)                                                                                                   \
   {                                                                                                                         \
-    bn_bwd_reduce_kernel<TDY, TX><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, R, C, rows_per_cta); \
+    bn_bwd_reduce_kernel<TDY, TX><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, R, C, rows_per_cta, lanes_x); \
     VPF_TRY(check_launch("bn_bwd_reduce_kernel"));                                                                          \
     bn_bwd_apply_kernel<TDY, TX, TDX><<<g2, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, (TDX *)dx, dgamma, dbeta, R, C); \
   }
+  if (dy_bf16 && x_bf16 && dx_bf16 && C % 8 == 0) {
+    bn_bwd_reduce_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, red, R, C, rows_per_cta, lanes_x);
+    VPF_TRY(check_launch("bn_bwd_reduce_kernel"));
+    bn_bwd_apply_bf16x8_kernel<<<grid_for((size_t)R * C / 8), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)x, scale, shift, mean, rstd, relu, red, (uint4 *)dx, dgamma, dbeta, R, C);
+  } else
   if (dy_bf16 && x_bf16 && dx_bf16) BNB(bf16, bf16, bf16)
   else if (!dy_bf16 && !x_bf16 && !dx_bf16) BNB(float, float, float)
   else if (dy_bf16 && !x_bf16 && dx_bf16) BNB(bf16, float, bf16)

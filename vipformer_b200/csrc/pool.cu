@@ -95,22 +95,42 @@ token_pool_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ ar
 
 // ------------------------------------------------------------ K = 3 linears
 // y = ((w.p + b) * scale + shift) ; pre (optional, bf16) gets y; act (optional, bf16) gets act(y)
+// one thread = 8 consecutive output channels of one row (16-byte stores); Co % 8 == 0
 __global__ void __launch_bounds__(256)
 linear3_fwd_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
                    const float *__restrict__ scale, const float *__restrict__ shift, bf16 *__restrict__ pre,
                    bf16 *__restrict__ actout, int act, long long R, int Co) {
-  const size_t total = (size_t)R * Co;
-  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-    const int c = (int)(e % Co);
+  const size_t total8 = (size_t)R * Co / 8;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total8; i += (size_t)gridDim.x * 256) {
+    const size_t e = i * 8;
+    const int c0 = (int)(e % Co);
     const size_t r = e / Co;
     const float *q = p + r * ldp;
-    float y = fmaf(w[c * 3 + 2], q[2], fmaf(w[c * 3 + 1], q[1], w[c * 3] * q[0])) + b[c];
-    if (scale) y = y * scale[c] + shift[c];
-    if (pre) pre[e] = __float2bfloat16(y);
+    const float x0 = q[0], x1 = q[1], x2 = q[2];
+    float y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      float t = fmaf(w[c * 3 + 2], x2, fmaf(w[c * 3 + 1], x1, w[c * 3] * x0)) + b[c];
+      if (scale) t = t * scale[c] + shift[c];
+      y[k] = t;
+    }
+    uint4 u;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+    if (pre) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
+      *reinterpret_cast<uint4 *>(pre + e) = u;
+    }
     if (actout) {
-      if (act == VPF_ACT_RELU) y = fmaxf(y, 0.f);
-      else if (act == VPF_ACT_GELU) y = gelu_exact(y);
-      actout[e] = __float2bfloat16(y);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (act == VPF_ACT_RELU) y[k] = fmaxf(y[k], 0.f);
+        else if (act == VPF_ACT_GELU) y[k] = gelu_exact(y[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
+      *reinterpret_cast<uint4 *>(actout + e) = u;
     }
   }
 }
@@ -120,13 +140,15 @@ __global__ void __launch_bounds__(256)
 linear3_stats_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
                      double *__restrict__ stats, long long R, int Co, int rows_per_cta) {
   const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  for (int c = threadIdx.x; c < Co; c += 256) {
+  const int lx = min(Co, 256), ny = 256 / lx, ty = threadIdx.x / lx;   // ty strides rows: no idle threads when Co < 256
+  if (ty >= ny) return;
+  for (int c = threadIdx.x % lx; c < Co; c += lx) {
     const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = b[c];
     double a = 0.0, q = 0.0;
-    for (long long r0 = row0; r0 < row1; r0 += 64) {
+    for (long long r0 = row0 + ty; r0 < row1; r0 += 64LL * ny) {
       float pa = 0.f, pq = 0.f;
-      const long long r1 = min(row1, r0 + 64);
-      for (long long r = r0; r < r1; ++r) {
+      const long long r1 = min(row1, r0 + 64LL * ny);
+      for (long long r = r0; r < r1; r += ny) {
         const float *x = p + (size_t)r * ldp;
         const float y = fmaf(w2, x[2], fmaf(w1, x[1], w0 * x[0])) + bb;
         pa += y; pq += y * y;
@@ -144,9 +166,11 @@ __global__ void __launch_bounds__(256)
 linear3_bwd_kernel(const Tdy *__restrict__ dy, const float *__restrict__ p, int ldp, float *__restrict__ dW,
                    float *__restrict__ db, long long R, int Co, int rows_per_cta) {
   const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  for (int c = threadIdx.x; c < Co; c += 256) {
+  const int lx = min(Co, 256), ny = 256 / lx, ty = threadIdx.x / lx;
+  if (ty >= ny) return;
+  for (int c = threadIdx.x % lx; c < Co; c += lx) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
-    for (long long r = row0; r < row1; ++r) {
+    for (long long r = row0 + ty; r < row1; r += ny) {
       float d;
       if constexpr (sizeof(Tdy) == 4) d = dy[(size_t)r * Co + c]; else d = __bfloat162float(dy[(size_t)r * Co + c]);
       const float *x = p + (size_t)r * ldp;
@@ -167,17 +191,19 @@ linear3_bn_bwd_kernel(const bf16 *__restrict__ dh, const float *__restrict__ p, 
                       const float *__restrict__ mean, const float *__restrict__ rstd, double *__restrict__ red,
                       float *__restrict__ dW, float *__restrict__ db, long long R, int Co, int rows_per_cta) {
   const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  for (int c = threadIdx.x; c < Co; c += 256) {
+  const int lx = min(Co, 256), ny = 256 / lx, ty = threadIdx.x / lx;
+  if (ty >= ny) return;
+  for (int c = threadIdx.x % lx; c < Co; c += lx) {
     const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = b[c];
     const float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
     float m1 = 0.f, m2 = 0.f;
     if (PHASE == 2) { m1 = (float)(red[c] / (double)R); m2 = (float)(red[Co + c] / (double)R); }
     double a = 0.0, q = 0.0;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
-    for (long long r0 = row0; r0 < row1; r0 += 64) {
+    for (long long r0 = row0 + ty; r0 < row1; r0 += 64LL * ny) {
       float pa = 0.f, pq = 0.f;
-      const long long r1 = min(row1, r0 + 64);
-      for (long long r = r0; r < r1; ++r) {
+      const long long r1 = min(row1, r0 + 64LL * ny);
+      for (long long r = r0; r < r1; r += ny) {
         const float *x = p + (size_t)r * ldp;
         const float y = fmaf(w2, x[2], fmaf(w1, x[1], w0 * x[0])) + bb;
         float d = __bfloat162float(dh[(size_t)r * Co + c]);
@@ -277,8 +303,9 @@ int vpf_linear3_fwd(const float *p, int ldp, const float *w, const float *b, con
                     void *pre_bf16, void *act_bf16, int act, long long R, int Co, void *stream) {
   VPF_REQUIRE(p && w && b && (pre_bf16 || act_bf16), "linear3_fwd: null pointer");
   VPF_REQUIRE((scale == nullptr) == (shift == nullptr), "linear3_fwd: scale/shift must come together");
+  VPF_REQUIRE(Co % 8 == 0, "linear3_fwd: Co=%d must be a multiple of 8", Co);
   if (R == 0) return VPF_OK;
-  linear3_fwd_kernel<<<grid_for((size_t)R * Co), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, scale, shift, (bf16 *)pre_bf16, (bf16 *)act_bf16, act, R, Co);
+  linear3_fwd_kernel<<<grid_for((size_t)R * Co / 8), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, scale, shift, (bf16 *)pre_bf16, (bf16 *)act_bf16, act, R, Co);
   return check_launch("linear3_fwd_kernel");
 }
 
