@@ -3,11 +3,11 @@
 //   C[M,N] (op)= epilogue( alpha * sum_k A(m,k) * B(n,k) )
 //
 // Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 6-stage ring)
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 5-stage ring)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128 N=128 K=16; accumulators in TMEM,
 //                               two 128-column accumulator stages so the epilogue of tile i
 //                               overlaps the main loop of tile i+1)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> smem transpose -> fused epilogue -> coalesced global)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b -> registers -> smem transpose -> fused epilogue -> coalesced global)
 //
 // Both operands may be K-major (row-major [rows][K]) or MN-major ([K][rows]); that covers the
 // forward (X.W^T), the data gradient (dY.W) and the weight gradient (dY^T.X, split-K with
@@ -21,12 +21,12 @@
 namespace vpf {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kTileBytesA = BM * BK * 2, kTileBytesB = BN * BK * 2;
 constexpr int kStageBytes = kTileBytesA + kTileBytesB;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kStgLd = 36;   // padded row stride (floats) of the per-warp epilogue transpose tile
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4 /*epilogue staging*/;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * kStgLd * 4 /*epilogue staging*/;
 constexpr int kTmemCols = 2 * BN;
 
 struct GemmArgs {
@@ -36,9 +36,29 @@ struct GemmArgs {
   vpf_gemm_epilogue e;
 };
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (nn.GELU default, partseg.py:196) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// the bf16 rounding of the stored result); one MUFU.EX2 + one MUFU.RCP instead of the ~30-instruction erff().
+__device__ __forceinline__ void erf_parts(float x, float &erf_v, float &gauss) {
+  // for z = x / sqrt(2): erf(z) and exp(-z^2) = exp(-x^2 / 2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  gauss = __expf(-z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * gauss;
+  erf_v = copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float er, ga;
+  erf_parts(x, er, ga);
+  return 0.5f * x * (1.0f + er);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+  float er, ga;
+  erf_parts(x, er, ga);
+  return 0.5f * (1.0f + er) + x * 0.39894228040143268f * ga;
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -61,7 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1) {
     if (ptx::elect_one()) {
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -169,8 +189,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       ptx::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
       ptx::tc_fence_after();
       const long long row0 = (long long)m_tile * BM + quad * 32;   // first row of this warp's 32-row slab
+      const int c_begin = ((warp - 2) >> 2) * (BN / 2);   // warps 2..5 take columns 0..63, warps 6..9 columns 64..127
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
         uint32_t r[32];
         __syncwarp();
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c, r);
@@ -212,113 +233,119 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int col = col0 + cq;
         if (col >= g.N) continue;
         const int nv = min(4, g.N - col);
-        float b4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (e.bias) {
+        if (vec_ok && nv == 4 && (e.aux_mode == VPF_AUX_NONE || (e.ld_aux & 3) == 0)) {
+          // ---------------- fast path: whole float4 quads.  All global loads of the chunk are issued up front
+          // (one epilogue warp has nobody to hide its latency behind), then the math, then the stores.
+          float4 t[8];
+          bool ok[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < nv) b4[q] = __ldg(e.bias + col + q);
+          for (int it = 0; it < 8; ++it) {
+            t[it] = *reinterpret_cast<const float4 *>(stg + (it * 4 + rsub) * kStgLd + cq);
+            ok[it] = row0 + it * 4 + rsub < g.M;
+          }
+          float4 rv[8], rg[8];
+          uint2 ax[8];
+          if (e.mode == VPF_EPI_RESIDUAL) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (ok[it]) rv[it] = __ldg(reinterpret_cast<const float4 *>(e.resid + (size_t)(row0 + it * 4 + rsub) * e.ldc + col));
+          }
+          if (e.aux_mode != VPF_AUX_NONE) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (ok[it]) ax[it] = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(e.aux) + (size_t)(row0 + it * 4 + rsub) * e.ld_aux + col));
+          }
+          if (e.rg_bias) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (ok[it]) rg[it] = __ldg(reinterpret_cast<const float4 *>(e.rg_bias + (size_t)((row0 + it * 4 + rsub) >> e.rg_shift) * e.rg_ld + col));
+          }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (!ok[it]) continue;
+            const long long grow = row0 + it * 4 + rsub;
+            const size_t off = (size_t)grow * e.ldc + col;
+            float v[4] = {t[it].x + b4.x, t[it].y + b4.y, t[it].z + b4.z, t[it].w + b4.w};
+            if (e.rg_bias) { v[0] += rg[it].x; v[1] += rg[it].y; v[2] += rg[it].z; v[3] += rg[it].w; }
+            if (e.out2) {
+              uint2 pk;
+              *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+              *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+              *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(e.out2) + off) = pk;
+            }
+            if (e.act == VPF_ACT_RELU) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (e.act == VPF_ACT_GELU) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = gelu_f(v[q]);
+            }
+            if (e.aux_mode != VPF_AUX_NONE) {
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ax[it].x));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ax[it].y));
+              const float a[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                v[q] = e.aux_mode == VPF_AUX_GELU_GRAD ? v[q] * gelu_grad_f(a[q]) : (a[q] > 0.f ? v[q] : 0.f);
+            }
+            if (e.mode == VPF_EPI_STORE) {
+              if (e.out_f32) {
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + off) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(e.out) + off) = pk;
+              }
+            } else if (e.mode == VPF_EPI_RESIDUAL) {   // out_f32 = resid + dropout(v)   (Residual, partseg.py:208-213)
+              if (drop_thr) {
+                const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = rng::keep(drop_key, ebase + q, drop_thr) ? v[q] * drop_scale : 0.f;
+              }
+              v[0] += rv[it].x; v[1] += rv[it].y; v[2] += rv[it].z; v[3] += rv[it].w;
+              *reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + off) = make_float4(v[0], v[1], v[2], v[3]);
+              if (e.out_bf16) {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(e.out_bf16) + off) = pk;
+              }
+            } else {   // VPF_EPI_ATOMIC_ADD: split-K weight gradients accumulate into the flat fp32 grad buffer
+              ptx::red_add_v4(reinterpret_cast<float *>(e.out) + off, v[0], v[1], v[2], v[3]);
+            }
+          }
+          continue;
         }
-#pragma unroll 2
+        // ---------------- generic path (ragged N, unaligned ld): scalar, element by element
         for (int it = 0; it < 8; ++it) {
           const int rl = it * 4 + rsub;
           const long long grow = row0 + rl;
           if (grow >= g.M) continue;
-          const float4 t = *reinterpret_cast<const float4 *>(stg + rl * kStgLd + cq);
-          float v[4] = {t.x + b4[0], t.y + b4[1], t.z + b4[2], t.w + b4[3]};
-          const bool full = vec_ok && nv == 4;
-          if (e.rg_bias) {
-            const float *rb = e.rg_bias + (size_t)(grow >> e.rg_shift) * e.rg_ld + col;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < nv) v[q] += __ldg(rb + q);
-          }
-          const size_t off = (size_t)grow * e.ldc + col;
-          if (e.out2) {
-            __nv_bfloat16 *o2 = reinterpret_cast<__nv_bfloat16 *>(e.out2) + off;
-            if (full) {
-              uint2 pk;
-              *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
-              *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
-              *reinterpret_cast<uint2 *>(o2) = pk;
+          for (int q = 0; q < nv; ++q) {
+            float v = stg[rl * kStgLd + cq + q];
+            const size_t off = (size_t)grow * e.ldc + col + q;
+            if (e.bias) v += __ldg(e.bias + col + q);
+            if (e.rg_bias) v += __ldg(e.rg_bias + (size_t)(grow >> e.rg_shift) * e.rg_ld + col + q);
+            if (e.out2) reinterpret_cast<__nv_bfloat16 *>(e.out2)[off] = __float2bfloat16(v);
+            if (e.act == VPF_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (e.act == VPF_ACT_GELU) v = gelu_f(v);
+            if (e.aux_mode != VPF_AUX_NONE) {
+              const float a = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(e.aux)[(size_t)grow * e.ld_aux + col + q]);
+              v = e.aux_mode == VPF_AUX_GELU_GRAD ? v * gelu_grad_f(a) : (a > 0.f ? v : 0.f);
+            }
+            if (e.mode == VPF_EPI_STORE) {
+              if (e.out_f32) reinterpret_cast<float *>(e.out)[off] = v;
+              else reinterpret_cast<__nv_bfloat16 *>(e.out)[off] = __float2bfloat16(v);
+            } else if (e.mode == VPF_EPI_RESIDUAL) {
+              if (drop_thr) v = rng::keep(drop_key, (uint32_t)((size_t)grow * g.N + col + q), drop_thr) ? v * drop_scale : 0.f;
+              v += e.resid[off];
+              reinterpret_cast<float *>(e.out)[off] = v;
+              if (e.out_bf16) reinterpret_cast<__nv_bfloat16 *>(e.out_bf16)[off] = __float2bfloat16(v);
             } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) o2[q] = __float2bfloat16(v[q]);
-            }
-          }
-          if (e.act == VPF_ACT_RELU) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
-          } else if (e.act == VPF_ACT_GELU) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = gelu_f(v[q]);
-          }
-          if (e.aux_mode != VPF_AUX_NONE) {
-            const __nv_bfloat16 *ax = reinterpret_cast<const __nv_bfloat16 *>(e.aux) + (size_t)grow * e.ld_aux + col;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            if (nv == 4 && (e.ld_aux & 3) == 0) {
-              const uint2 pk = *reinterpret_cast<const uint2 *>(ax);
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.x));
-              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.y));
-              a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) a[q] = __bfloat162float(ax[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              v[q] = e.aux_mode == VPF_AUX_GELU_GRAD ? v[q] * gelu_grad_f(a[q]) : (a[q] > 0.f ? v[q] : 0.f);
-          }
-          if (e.mode == VPF_EPI_STORE) {
-            if (e.out_f32) {
-              float *o = reinterpret_cast<float *>(e.out) + off;
-              if (full) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (q < nv) o[q] = v[q];
-              }
-            } else {
-              __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(e.out) + off;
-              if (full) {
-                uint2 pk;
-                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
-                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
-                *reinterpret_cast<uint2 *>(o) = pk;
-              } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (q < nv) o[q] = __float2bfloat16(v[q]);
-              }
-            }
-          } else if (e.mode == VPF_EPI_RESIDUAL) {
-            // out_f32 = resid + dropout(v)     (partseg.py:208-213 Residual)
-            const float *rs = e.resid + off;
-            float *o = reinterpret_cast<float *>(e.out) + off;
-            float rv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full) { const float4 q4 = *reinterpret_cast<const float4 *>(rs); rv[0] = q4.x; rv[1] = q4.y; rv[2] = q4.z; rv[3] = q4.w; }
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) rv[q] = rs[q];
-            }
-            if (drop_thr) {
-              const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) v[q] = rng::keep(drop_key, ebase + q, drop_thr) ? v[q] * drop_scale : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] += rv[q];
-            if (full) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) o[q] = v[q];
-            }
-            if (e.out_bf16) {
-              __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(e.out_bf16) + off;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) ob[q] = __float2bfloat16(v[q]);
-            }
-          } else {  // VPF_EPI_ATOMIC_ADD: split-K weight gradients accumulate into the flat fp32 grad buffer
-            float *o = reinterpret_cast<float *>(e.out) + off;
-            if (full) ptx::red_add_v4(o, v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) if (q < nv) atomicAdd(o + q, v[q]);
+              atomicAdd(reinterpret_cast<float *>(e.out) + off, v);
             }
           }
         }
