@@ -225,10 +225,12 @@ def run_ours(args):
     d2h = eng.losses_host.numel() * 4
 
     out = None
+    pk, pk_kind = peaks()
+    # roofline of the dominant kernel (tcgen05 GEMM): eager steps with CUDA events around every GEMM launch.  The step
+    # contains collectives when world > 1, so EVERY rank runs it; rank 0 reports.
+    roof = gemm_roofline(eng, load, pk, pk_kind)
+    barrier()
     if rank == 0:
-        pk, pk_kind = peaks()
-        # ---- roofline of the dominant kernel (tcgen05 GEMM): eager step with CUDA events around every GEMM launch
-        roof = gemm_roofline(eng, load, pk, pk_kind)
         tok = tokenizer_rate(dev, pk)
         cpu_rate, cpu_ms, threads = cpu_reference_step_rate(16, 3, 1)
         out = {
