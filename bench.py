@@ -153,7 +153,7 @@ def run_ours(args):
     cfg = dict(CFG, b=b)
     pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)     # script values (scripts/pretrain/*.sh)
     eng = PretrainEngine(pc, im, batch_pairs=b, num_points=cfg["N"], img_size=cfg["img"], lr=1e-3, seed=1,
-                         use_cuda_graph=not args.no_graph)
+                         use_cuda_graph=(not args.no_graph) and (world == 1 or args.graph))
     g = torch.Generator(device=dev).manual_seed(100 + rank)
 
     def synth_clouds(n):
@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU (weak scaling)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also with world_size > 1 (default: eager there)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
