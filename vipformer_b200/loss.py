@@ -22,6 +22,19 @@ def _dist():
     return None
 
 
+def shard_layout(rank, world, b):
+    """Column layout of the all-gathered embeddings: cat(all ranks' out0 blocks, all ranks' out1 blocks).
+    Returns (col_offset, half): local row i < b sits at column col_offset + i, row b + i at half + col_offset + i."""
+    return rank * b, world * b
+
+
+def self_pos_columns(i, b, col_offset, half):
+    """(own column, positive column) of local row i -- the host-side statement of `self_pos` in loss_optim.cu."""
+    if i < b:
+        return col_offset + i, half + col_offset + i
+    return half + col_offset + (i - b), col_offset + (i - b)
+
+
 def _stack2(a, b):
     """[a; b] as one contiguous fp32 [2b, D] buffer (copy kernels, no ATen cat)."""
     n, D = a.shape
@@ -45,7 +58,7 @@ class _NTXentCore:
             zc = torch.empty((2 * W * b, D), dtype=F32, device=x.device)
             dist.all_gather_into_tensor(zc[:W * b], z[:b].contiguous())
             dist.all_gather_into_tensor(zc[W * b:], z[b:].contiguous())
-            col_offset, half = r * b, W * b
+            col_offset, half = shard_layout(r, W, b)
         else:
             zc, col_offset, half = z, 0, b
         loss = ops.zeros_(torch.empty(1, dtype=F32, device=x.device))
