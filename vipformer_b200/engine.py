@@ -51,7 +51,8 @@ class PretrainEngine:
         self.lr = torch.tensor([lr], dtype=F32, device=self.device)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.temperature, self.cmid_weight = temperature, cmid_weight
-        self.state = runtime.StepState.get(self.device)
+        self.state = runtime.StepState.get(self.device)   # one engine per process/GPU, like the reference's mp.spawn
+        self.state[0] = 0                                  # optimizer step count (AdamW bias correction)
         runtime.manual_seed(seed * 1000003 + self.rank, self.device)
         b = batch_pairs
         self.b, self.N = b, num_points
