@@ -187,6 +187,10 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
 int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale,
                const float *shift, const float *mean, const float *rstd, int relu, double *red,
                void *dx, int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream);
+/* nn.GELU (exact erf) of the MLP, partseg.py:196, as streaming kernels: h = gelu(z); dz = dh * gelu'(z) with the
+ * column sums of dz (bias gradient) accumulated into colsum (optional). */
+int vpf_gelu_fwd(const void *z_bf16, void *h_bf16, long long n, void *stream);
+int vpf_gelu_bwd(const void *dh_bf16, const void *z_bf16, void *dz_bf16, float *colsum, long long R, int C, void *stream);
 int vpf_cast_bf16(const float *x, void *y_bf16, long long n, void *stream);
 int vpf_fill_zero(void *p, long long bytes, void *stream);
 

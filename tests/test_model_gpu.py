@@ -122,7 +122,10 @@ def test_dropout_training_step_changes_with_seed(runs):
     b, _ = pc(pts)
     rt.manual_seed(2)
     c, _ = pc(pts)
-    assert torch.equal(a, b) and not torch.equal(a, c)
+    # same seed => same masks (outputs equal up to the last-bit nondeterminism of the atomically reduced BatchNorm
+    # statistics); a different seed draws different masks
+    same, diff = relfro(a, b), relfro(a, c)
+    assert same < 0.05 and diff > 0.2 and diff > 4 * same, (same, diff)
     a.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pc.parameters())
 

@@ -357,3 +357,18 @@ def test_adamw_matches_torch():
     close(p, ref.detach(), tol=1e-5)
     assert torch.equal(shadow.float(), p.to(BF16).float())
     assert state[0].item() == 3 and state[1].item() != 123
+
+
+def test_gelu_streaming_kernels():
+    from vipformer_b200 import ops
+
+    z = rnd((3000, 512), 1, BF16, scale=2.0)
+    h = ops.gelu_fwd(z)
+    close(h, F.gelu(z.float()), bf16=True)
+    dh = rnd((3000, 512), 2, BF16)
+    cs = torch.zeros(512, device="cuda")
+    dz = ops.gelu_bwd(dh, z, colsum=cs)
+    zf = z.float().requires_grad_(True)
+    F.gelu(zf).backward(dh.float())
+    close(dz, zf.grad, bf16=True)
+    close(cs, dz.float().sum(0), tol=2e-3)

@@ -1,0 +1,29 @@
+// gelu.cuh -- exact-erf GELU and its derivative (shared by the GEMM epilogue and the streaming kernels)
+#pragma once
+
+namespace vpf {
+
+// exact-erf GELU (nn.GELU default, partseg.py:196) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// the bf16 rounding of the stored result); one MUFU.EX2 + one MUFU.RCP instead of the ~30-instruction erff().
+__device__ __forceinline__ void erf_parts(float x, float &erf_v, float &gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;   // erf(x / sqrt 2), exp(-x^2 / 2)
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  gauss = __expf(-z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  erf_v = copysignf(1.0f - p * t * gauss, x);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float er, ga;
+  erf_parts(x, er, ga);
+  return 0.5f * x * (1.0f + er);
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float er, ga;
+  erf_parts(x, er, ga);
+  return 0.5f * (1.0f + er) + x * 0.39894228040143268f * ga;
+}
+
+}  // namespace vpf

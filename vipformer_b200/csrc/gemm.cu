@@ -6,8 +6,8 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage ring of (A,B) k-blocks
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1, M=128 N=128 K=16, accumulators in TMEM; two 128-column
 //                              accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..9  epilogue       two groups of 4 warps (one warp per TMEM lane quadrant), each group owning 64 of the
-//                              tile's 128 columns.  Everything the epilogue touches in HBM moves by TMA:
+//   warps 2..17 epilogue       two groups of 8 warps, each group owning 64 of the tile's 128 columns (one warp per
+//                              TMEM lane quadrant and 32-column chunk).  Everything the epilogue touches in HBM moves by TMA:
 //                                - residual (fp32) and aux (bf16: saved pre-activation / ReLU source) tiles are
 //                                  PREFETCHED into shared memory while the MMA of the same tile is still running,
 //                                - results are written to a 128B-swizzled staging tile and leave by
@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "rng.cuh"
+#include "gelu.cuh"
 
 namespace vpf {
 
@@ -30,7 +31,7 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 4;
 constexpr int kTileBytesA = BM * BK * 2, kTileBytesB = BN * BK * 2;
 constexpr int kStageBytes = kTileBytesA + kTileBytesB;
-constexpr int kGemmThreads = 320;
+constexpr int kGemmThreads = 576;   // TMA warp + MMA warp + 16 epilogue warps
 constexpr int kBoxBytes = 128 * 128;              // one staging box: 128 rows x 128 bytes (32 fp32 or 64 bf16 columns)
 constexpr int kStgF32 = 4 * kBoxBytes;            // fp32 tile: 4 boxes of 32 columns            (64 KB)
 constexpr int kStgAux = 2 * kBoxBytes;            // bf16 tile: 2 boxes of 64 columns            (32 KB)
@@ -47,29 +48,6 @@ struct GemmArgs {
   int tma_epi;   // 1: TMA epilogue (aligned outputs); 0: generic direct-global epilogue
   vpf_gemm_epilogue e;
 };
-
-// exact-erf GELU (nn.GELU default, partseg.py:196) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
-// the bf16 rounding of the stored result); one MUFU.EX2 + one MUFU.RCP instead of the ~30-instruction erff().
-__device__ __forceinline__ void erf_parts(float x, float &erf_v, float &gauss) {
-  const float z = fabsf(x) * 0.70710678118654752f;   // erf(x / sqrt 2), exp(-x^2 / 2)
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  gauss = __expf(-z * z);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  erf_v = copysignf(1.0f - p * t * gauss, x);
-}
-__device__ __forceinline__ float gelu_f(float x) {
-  float er, ga;
-  erf_parts(x, er, ga);
-  return 0.5f * x * (1.0f + er);
-}
-__device__ __forceinline__ float gelu_grad_f(float x) {
-  float er, ga;
-  erf_parts(x, er, ga);
-  return 0.5f * (1.0f + er) + x * 0.39894228040143268f * ga;
-}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -119,7 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1) {
     if (ptx::elect_one()) {
       for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); ptx::mbar_init(&ld_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 16); ptx::mbar_init(&ld_bar[s], 1); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -202,10 +180,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ---------------------------------------------------------------- epilogue
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    const int grp = (warp - 2) >> 2;        // column half of the tile this group of 4 warps owns
+    const int grp = (warp - 2) >> 3;        // column half (64 columns) of the tile this group of 8 warps owns
+    const int c2 = ((warp - 2) >> 2) & 1;   // which 32-column chunk of that half this warp handles
     const int row = quad * 32 + lane;       // this thread's row inside the 128-row tile
-    const bool leader = (warp - 2) == grp * 4 && lane == 0;
+    const bool leader = (warp - 2) == grp * 8 && lane == 0;
     const int bar_id = 1 + grp;
+    constexpr int kGrpThreads = 256;
     uint8_t *stg = smem + kOffStg, *stg_aux = smem + kOffAux;
     const bool gm = e.gm_S > 0;
     const bool out_is_f32 = e.mode != VPF_EPI_STORE || e.out_f32;
@@ -233,11 +213,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const long long grow = (long long)tile_row0 + row;
       const bool grp_active = colg0 < g.N;                 // uniform over the group
 
-      if (g.tma_epi) {
-        // staging is free once the previous tile's bulk stores have READ it; then prefetch residual / aux tiles
+      if (g.tma_epi && need_ld) {
+        // residual / aux tiles are prefetched into the staging area while the MMA of this tile is still running;
+        // the staging is free once the previous tile's bulk stores have READ it
         if (leader) bulk_wait_read0();
-        named_bar_sync(bar_id, 128);
-        if (need_ld && leader && grp_active) {
+        named_bar_sync(bar_id, kGrpThreads);
+        if (leader && grp_active) {
           uint32_t bytes = 0;
           if (e.mode == VPF_EPI_RESIDUAL) bytes += 2 * kBoxBytes;
           if (e.aux_mode != VPF_AUX_NONE) bytes += kBoxBytes;
@@ -255,9 +236,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         ptx::mbar_wait(&ld_bar[grp], ld_phase);
         ld_phase ^= 1;
       }
+      if (g.tma_epi && !need_ld) {
+        // nothing to prefetch: only now (after the accumulator wait, so the previous tile's bulk store has had the whole
+        // main loop to drain) make sure the staging area has been read
+        if (leader) bulk_wait_read0();
+        named_bar_sync(bar_id, kGrpThreads);
+      }
 
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
+      do {
         uint32_t r[32];
         __syncwarp();
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + grp * 64 + c2 * 32, r);
@@ -376,7 +362,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             *reinterpret_cast<uint4 *>(bf_out_box + swz(row, c2 * 4 + k)) = pk;
           }
         }
-      }
+      } while (0);
       // accumulator stage can be refilled by the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -384,7 +370,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
       if (g.tma_epi && grp_active) {
         ptx::fence_proxy_async();            // make the generic-proxy smem writes visible to the TMA unit
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, kGrpThreads);
         if (leader) {
           if (e.out) {
             if (e.mode == VPF_EPI_ATOMIC_ADD) {
@@ -403,14 +389,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (gm) {
           // per-patch max over gm_S rows on the fp32 accumulators, first index wins (torch.max, utils.py:180,188).
           // thread t of the group: column t % 64, row half t / 64.
-          const int t = (warp - 2 - grp * 4) * 32 + lane;
+          const int t = (warp - 2 - grp * 8) * 32 + lane;
           const int cl = t & 63, col = colg0 + cl;
           if (col < g.N) {
             const float badd = e.bias ? __ldg(e.bias + col) : 0.f;
             const uint8_t *box = f32_box + (cl >> 5) * kBoxBytes;
             const int k = (cl & 31) >> 2, sub = (cl & 3) * 4;
             const int S = e.gm_S;
-            for (int r0 = (t >> 6) * 64; r0 < (t >> 6) * 64 + 64; r0 += S) {
+            for (int r0 = (t >> 6) * 32; r0 < (t >> 6) * 32 + 32; r0 += S) {
               if (tile_row0 + r0 >= g.M) break;
               float m = *reinterpret_cast<const float *>(box + swz(r0, k) + sub);
               int am = 0;
@@ -483,8 +469,8 @@ using namespace vpf;
 extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb, int M, int N, int K,
                              int splits, const vpf_gemm_epilogue *epi, void *stream) {
   VPF_REQUIRE(A && B && epi && (epi->out || epi->gm_S > 0), "gemm: null pointer");
-  VPF_REQUIRE(epi->gm_S == 0 || ((epi->gm_S & (epi->gm_S - 1)) == 0 && epi->gm_S <= 64 && M % epi->gm_S == 0 && epi->mode == VPF_EPI_STORE && epi->alpha == 1.0f),
-              "gemm: max-pool epilogue needs S a power of two <= 64 dividing M, store mode, alpha 1");
+  VPF_REQUIRE(epi->gm_S == 0 || ((epi->gm_S & (epi->gm_S - 1)) == 0 && epi->gm_S <= 32 && M % epi->gm_S == 0 && epi->mode == VPF_EPI_STORE && epi->alpha == 1.0f),
+              "gemm: max-pool epilogue needs S a power of two <= 32 dividing M, store mode, alpha 1");
   VPF_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   VPF_REQUIRE(epi->mode == VPF_EPI_STORE || epi->mode == VPF_EPI_RESIDUAL || epi->mode == VPF_EPI_ATOMIC_ADD, "gemm: bad epilogue mode %d", epi->mode);
   VPF_REQUIRE(epi->mode != VPF_EPI_RESIDUAL || epi->resid, "gemm: residual epilogue needs resid");

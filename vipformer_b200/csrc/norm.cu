@@ -6,6 +6,7 @@
 //   nn.Dropout inside Residual                     partseg.py:201-213
 #include "common.cuh"
 #include "rng.cuh"
+#include "gelu.cuh"
 
 namespace vpf {
 
@@ -452,6 +453,66 @@ colreduce_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *
   }
 }
 
+// h = gelu(z), 8 bf16 per thread (nn.GELU of the MLP, partseg.py:196).  Runs at full occupancy, which hides the
+// MUFU/FMA latency chains that a 16-warp GEMM epilogue cannot.
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const uint4 *__restrict__ z, uint4 *__restrict__ h, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    float f[8];
+    unpack8(__ldg(z + i), f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = gelu_f(f[q]);
+    h[i] = pack8(f);
+  }
+}
+
+// dz = dh * gelu'(z);  colsum += column sums of dz (the bias gradient of the first MLP Linear)
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16 *__restrict__ dh, const __nv_bfloat16 *__restrict__ z, __nv_bfloat16 *__restrict__ dz,
+                float *__restrict__ colsum, long long R, int C, int rows_per_cta) {
+  extern __shared__ float s_red[];   // [cgx*8]
+  const ColMap m = col_map(C);
+  const int ncol_cta = m.cgx * 8;
+  for (int i = threadIdx.x; i < ncol_cta; i += 256) s_red[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+    for (long long r = row0 + m.ty; r < row1; r += 2LL * m.ny) {
+      uint4 ud[2], uz[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long long rr = r + (long long)k * m.ny;
+        if (rr < row1) { ud[k] = ldg16(dh + (size_t)rr * C + m.col); uz[k] = ldg16(z + (size_t)rr * C + m.col); }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long long rr = r + (long long)k * m.ny;
+        if (rr >= row1) continue;
+        float d[8], zz[8];
+        unpack8(ud[k], d);
+        unpack8(uz[k], zz);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { d[q] *= gelu_grad_f(zz[q]); acc[q] += d[q]; }
+        *reinterpret_cast<uint4 *>(dz + (size_t)rr * C + m.col) = pack8(d);
+      }
+    }
+    if (colsum) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) atomicAdd(&s_red[m.tx * 8 + q], acc[q]);
+    }
+  }
+  __syncthreads();
+  if (colsum) {
+    for (int i = threadIdx.x; i < ncol_cta; i += 256) {
+      const int c = blockIdx.y * ncol_cta + i;
+      if (c < C) atomicAdd(colsum + c, s_red[i]);
+    }
+  }
+}
+
 // fm[0..C) = sum_dyb / R, fm[C..2C) = sum_dyb_xhat / R (fp32, for the apply pass); dgamma/dbeta accumulate
 __global__ void bn_bwd_means_kernel(const double *__restrict__ red, float *__restrict__ fm, float *__restrict__ dgamma,
                                     float *__restrict__ dbeta, long long R, int C) {
@@ -635,6 +696,24 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
   else return fail(VPF_EINVAL, "bn_bwd: unsupported dtype combination");
 #undef BNB
   return check_launch("bn_bwd_apply_kernel");
+}
+
+int vpf_gelu_fwd(const void *z_bf16, void *h_bf16, long long n, void *stream) {
+  VPF_REQUIRE(z_bf16 && h_bf16, "gelu_fwd: null pointer");
+  VPF_REQUIRE(n % 8 == 0, "gelu_fwd: n=%lld must be a multiple of 8", n);
+  if (n == 0) return VPF_OK;
+  gelu_fwd_kernel<<<grid_for((size_t)n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4 *)z_bf16, (uint4 *)h_bf16, (size_t)n / 8);
+  return check_launch("gelu_fwd_kernel");
+}
+
+int vpf_gelu_bwd(const void *dh_bf16, const void *z_bf16, void *dz_bf16, float *colsum, long long R, int C, void *stream) {
+  VPF_REQUIRE(dh_bf16 && z_bf16 && dz_bf16, "gelu_bwd: null pointer");
+  VPF_REQUIRE(C % 8 == 0, "gelu_bwd: C=%d must be a multiple of 8", C);
+  if (R == 0 || C == 0) return VPF_OK;
+  dim3 g8; int rpc, smem;
+  bf16_col_cfg(R, C, g8, rpc, smem);
+  gelu_bwd_kernel<<<g8, 256, smem, (cudaStream_t)stream>>>((const bf16 *)dh_bf16, (const bf16 *)z_bf16, (bf16 *)dz_bf16, colsum, R, C, rpc);
+  return check_launch("gelu_bwd_kernel");
 }
 
 int vpf_cast_bf16(const float *x, void *y_bf16, long long n, void *stream) {

@@ -95,6 +95,19 @@ def cast_bf16(x, out=None):
     return out
 
 
+def gelu_fwd(z):
+    h = torch.empty_like(z)
+    _lib.call("vpf_gelu_fwd", _p(z), _p(h), _ll(z.numel()), _s())
+    return h
+
+
+def gelu_bwd(dh, z, colsum=None):
+    R, C = z.shape
+    dz = torch.empty_like(z)
+    _lib.call("vpf_gelu_bwd", _p(dh), _p(z), _p(dz), _p(colsum), _ll(R), _i(C), _s())
+    return dz
+
+
 def add_scale(a, b, alpha, out=None):
     out = torch.empty_like(a) if out is None else out
     _lib.call("vpf_add_scale", _p(a), _p(b), _p(out), _f(alpha), _ll(a.numel()), _s())
