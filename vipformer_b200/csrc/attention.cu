@@ -111,20 +111,27 @@ __device__ __forceinline__ void pack_p(uint32_t (&p)[4][4], const float (&s)[8][
   }
 }
 
+// Attention-probability dropout (partseg.py:81).  One 32-bit hash covers a 2x2 block of (query, key) positions, 8 bits
+// each: whichever way a thread's accumulator elements are paired (adjacent keys in the forward / dQ kernels, adjacent
+// queries in the dK/dV kernel) two elements share one hash.  Effective p = round(256 p) / 256 (0.1 -> 26/256).
 struct DropCfg {
-  uint32_t thr, key;
+  uint32_t thr, key;   // thr: 8-bit threshold (0 = dropout off)
   float scale;
 };
 __device__ __forceinline__ DropCfg make_drop(float p, const unsigned long long *seed_ptr, uint32_t op_id) {
   DropCfg d;
-  d.thr = p > 0.f ? rng::threshold(p) : 0u;
+  d.thr = p > 0.f ? (uint32_t)(p * 256.f + 0.5f) : 0u;
   d.key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
-  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  d.scale = d.thr ? 256.f / (256.f - (float)d.thr) : 1.f;
   return d;
 }
-// element index of attention probability (bh, i, j)
-__device__ __forceinline__ uint32_t prob_index(int bh, int i, int j, int Lq, int Lk) {
-  return ((uint32_t)bh * (uint32_t)Lq + (uint32_t)i) * (uint32_t)Lk + (uint32_t)j;
+// hash of the 2x2 block containing (i, j); element (i, j) uses byte ((i & 1) << 1) | (j & 1)
+__device__ __forceinline__ uint32_t block_hash(const DropCfg &dc, int bh, int i, int j, int Lq, int Lk) {
+  const uint32_t idx = ((uint32_t)bh * (uint32_t)((Lq + 1) >> 1) + (uint32_t)(i >> 1)) * (uint32_t)((Lk + 1) >> 1) + (uint32_t)(j >> 1);
+  return rng::mix32(idx * 0x9e3779b1u ^ dc.key);
+}
+__device__ __forceinline__ bool keep_from(uint32_t hash, int i, int j, uint32_t thr) {
+  return ((hash >> ((((i & 1) << 1) | (j & 1)) * 8)) & 0xffu) >= thr;
 }
 
 // ------------------------------------------------------------------ forward
@@ -201,13 +208,19 @@ attn_fwd_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K,
     for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float p = exp2f(s[nb][e] - mx[e >> 1]);
+        const float p = exp2f(s[nb][e] - mx[e >> 1]);
         rs[e >> 1] += p;
-        if (dc.thr) {
-          const int i = r0 + (e >> 1) * 8, j = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
-          p = rng::keep(dc.key, prob_index(bh, i, j, Lq, Lk), dc.thr) ? p * dc.scale : 0.f;
-        }
         s[nb][e] = p;
+      }
+      if (dc.thr) {
+        const int j = k0 + nb * 8 + (lane & 3) * 2;   // even: (j, j+1) share a hash
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int i = r0 + q * 8;
+          const uint32_t hsh = block_hash(dc, bh, i, j, Lq, Lk);
+          s[nb][2 * q] = keep_from(hsh, i, j, dc.thr) ? s[nb][2 * q] * dc.scale : 0.f;
+          s[nb][2 * q + 1] = keep_from(hsh, i, j + 1, dc.thr) ? s[nb][2 * q + 1] * dc.scale : 0.f;
+        }
       }
     }
 #pragma unroll
@@ -331,20 +344,26 @@ attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict_
     mma_a_tileT(dp, va, tdO, lane);   // dP^T[key][q] = V dO^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
+      const int qe = nb * 8 + (lane & 3) * 2;   // even local query: (qe, qe+1) share a hash
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ql = nb * 8 + (lane & 3) * 2 + (e & 1);
-        const int j = jrow + (e >> 1) * 8;
-        float p = j < Lk ? exp2f(st[nb][e] * sc2 - tl[ql]) : 0.f;
-        float dpe = dp[nb][e];
-        float pd = p;
-        if (dc.thr) {
-          const bool keep = rng::keep(dc.key, prob_index(bh, q0 + ql, j, Lq, Lk), dc.thr);
-          pd = keep ? p * dc.scale : 0.f;
-          dpe = keep ? dpe * dc.scale : 0.f;
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int j = jrow + h2 * 8;
+        uint32_t hsh = 0;
+        if (dc.thr) hsh = block_hash(dc, bh, q0 + qe, j, Lq, Lk);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int e = h2 * 2 + w, ql = qe + w;
+          const float p = j < Lk ? exp2f(st[nb][e] * sc2 - tl[ql]) : 0.f;
+          float dpe = dp[nb][e];
+          float pd = p;
+          if (dc.thr) {
+            const bool keep = keep_from(hsh, q0 + ql, j, dc.thr);
+            pd = keep ? p * dc.scale : 0.f;
+            dpe = keep ? dpe * dc.scale : 0.f;
+          }
+          st[nb][e] = pd;                               // dropped P^T (for dV)
+          dp[nb][e] = p * (dpe - td[ql]) * scale;       // dS^T (for dK)
         }
-        st[nb][e] = pd;                               // dropped P^T (for dV)
-        dp[nb][e] = p * (dpe - td[ql]) * scale;       // dS^T (for dK)
       }
     }
     uint32_t pa[4][4];
@@ -430,13 +449,20 @@ attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__
     mma_a_tileT(dp, da, tV, lane);   // dP = dO V^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
+      const int je = k0 + nb * 8 + (lane & 3) * 2;   // even key: (je, je+1) share a hash
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
-        const float p = j < Lk ? exp2f(s[nb][e] * sc2 - lse[e >> 1]) : 0.f;
-        float dpe = dp[nb][e];
-        if (dc.thr) dpe = rng::keep(dc.key, prob_index(bh, r0 + (e >> 1) * 8, j, Lq, Lk), dc.thr) ? dpe * dc.scale : 0.f;
-        s[nb][e] = p * (dpe - dl[e >> 1]) * scale;  // dS
+      for (int q = 0; q < 2; ++q) {
+        const int i = r0 + q * 8;
+        uint32_t hsh = 0;
+        if (dc.thr) hsh = block_hash(dc, bh, i, je, Lq, Lk);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int e = q * 2 + w, j = je + w;
+          const float p = j < Lk ? exp2f(s[nb][e] * sc2 - lse[q]) : 0.f;
+          float dpe = dp[nb][e];
+          if (dc.thr) dpe = keep_from(hsh, i, j, dc.thr) ? dpe * dc.scale : 0.f;
+          s[nb][e] = p * (dpe - dl[q]) * scale;  // dS
+        }
       }
     }
     uint32_t pa[4][4];
