@@ -225,12 +225,13 @@ int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long 
 /* ------------------------------------------------------------------ loss + optimiser
  * NT-Xent (lightly 1.1.21 NTXentLoss; call sites pretrain.py:155,196,202). */
 int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *stream);
+/* S_ws: fp32 scratch [n_r, n_c] -- holds the logits after fwd (keep it for bwd, which overwrites it); G_ws [n_r, D]. */
 int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local,
-                   int col_offset, int half, float temperature, float *lse_out, float *loss_out,
-                   void *stream);
+                   int col_offset, int half, float temperature, float *S_ws, float *lse_out,
+                   float *loss_out, void *stream);
 int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all,
                    int n_c, int D, int b_local, int col_offset, int half, float temperature,
-                   float gscale, const float *upstream, float *dx, void *stream);
+                   float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream);
 /* torch.optim.AdamW step (pretrain.py:121-124,210) on a flat buffer, refreshing the bf16 shadow. */
 int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n,
               const float *lr_ptr, float beta1, float beta2, float eps, float weight_decay,

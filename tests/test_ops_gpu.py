@@ -299,12 +299,12 @@ def test_ntxent_fwd_bwd(b, D):
     x = torch.cat([x0, x1], 0).contiguous()
     z, norm = ops.l2norm_rows(x)
     loss = torch.zeros(1, device="cuda")
-    lse = ops.ntxent_fwd(z, z, b, 0, b, 0.1, loss)
+    lse, S = ops.ntxent_fwd(z, z, b, 0, b, 0.1, loss)
     xr0, xr1 = x0.clone().requires_grad_(True), x1.clone().requires_grad_(True)
     lref = ntxent_ref(xr0, xr1, 0.1)
     assert abs(loss.item() - lref.item()) < 1e-4 * max(1.0, abs(lref.item()))
     lref.backward()
-    dx = ops.ntxent_bwd(z, norm, z, lse, b, 0, b, 0.1, 1.0 / (2 * b))
+    dx = ops.ntxent_bwd(z, norm, z, lse, S, b, 0, b, 0.1, 1.0 / (2 * b))
     close(dx[:b], xr0.grad, tol=1e-3)
     close(dx[b:], xr1.grad, tol=1e-3)
 
@@ -325,15 +325,15 @@ def test_ntxent_global_negatives_matches_single_process():
         xl = torch.cat([x0[r * b:(r + 1) * b], x1[r * b:(r + 1) * b]], 0).contiguous()
         z, norm = ops.l2norm_rows(xl)
         loss = torch.zeros(1, device="cuda")
-        lse = ops.ntxent_fwd(z, zc, b, r * b, b * W, 0.1, loss)
+        lse, S = ops.ntxent_fwd(z, zc, b, r * b, b * W, 0.1, loss)
         losses.append(loss)
         lses.append(lse)
-        locals_.append((z, norm))
+        locals_.append((z, norm, S))
     assert abs(torch.stack(losses).mean().item() - lref.item()) < 1e-4 * max(1.0, abs(lref.item()))
     lse_all = torch.cat([torch.cat([l[:b] for l in lses]), torch.cat([l[b:] for l in lses])])
     for r in range(W):
-        z, norm = locals_[r]
-        dx = ops.ntxent_bwd(z, norm, zc, lse_all, b, r * b, b * W, 0.1, 1.0 / (2 * b * W))
+        z, norm, S = locals_[r]
+        dx = ops.ntxent_bwd(z, norm, zc, lse_all, S, b, r * b, b * W, 0.1, 1.0 / (2 * b * W))
         close(dx[:b], xr0.grad[r * b:(r + 1) * b], tol=1e-3)
         close(dx[b:], xr1.grad[r * b:(r + 1) * b], tol=1e-3)
 

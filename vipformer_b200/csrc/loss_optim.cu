@@ -1,5 +1,5 @@
-// loss_optim.cu -- NT-Xent contrastive objective (fused similarity -> online log-sum-exp ->
-// reduction; the [2b, 2b] logits never exist in memory) and the fused AdamW update.
+// loss_optim.cu -- NT-Xent contrastive objective (fp32 similarity GEMM -> masked row log-sum-exp -> reduction; the
+// backward reuses the logits scratch in place) and the fused AdamW update.
 //
 // NT-Xent restates lightly==1.1.21 lightly/loss/ntx_ent_loss.py (third-party, not vendored by the
 // reference; call sites pretrain.py:155,196,202):  rows = cat(normalize(out0), normalize(out1)),
@@ -35,82 +35,115 @@ __device__ __forceinline__ void self_pos(int i, int b_local, int col_offset, int
   else { self = half + col_offset + (i - b_local); pos = col_offset + (i - b_local); }
 }
 
-constexpr int kMaxDPerLane = 24;  // D <= 768
-
-// one warp per local row, lanes across the feature dim; online log-sum-exp over all columns
+// ---- tiled fp32 SIMT GEMM for the similarity matrix and its backward (sizes are tiny: 2b x 2bW x D).  fp32 on purpose:
+// logits are divided by T = 0.1, bf16 operands would put ~1e-2 of noise on them.
+//   b_nt = 1: C[M,N] = alpha * A[M,K] . B[N,K]^T        b_nt = 0: C[M,N] = alpha * A[M,K] . B[K,N]
+constexpr int kSgTile = 64, kSgK = 16;
 __global__ void __launch_bounds__(256)
-ntxent_fwd_kernel(const float *__restrict__ zr, int n_r, const float *__restrict__ zc, int n_c, int D, int b_local,
-                  int col_offset, int half, float invT, float *__restrict__ lse_out, float *__restrict__ loss_out) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= n_r) return;
-  const int nper = D / 32;
-  float a[kMaxDPerLane];
+sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K,
+             float alpha, int b_nt) {
+  __shared__ float sA[kSgK][kSgTile + 4], sB[kSgK][kSgTile + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * kSgTile, n0 = blockIdx.x * kSgTile;
+  float acc[4][4];
 #pragma unroll
-  for (int t = 0; t < kMaxDPerLane; ++t) a[t] = t < nper ? zr[(size_t)i * D + lane + 32 * t] : 0.f;
-  int self, pos;
-  self_pos(i, b_local, col_offset, half, self, pos);
-  float m = -INFINITY, l = 0.f, spos = 0.f;
-  for (int j = 0; j < n_c; ++j) {
-    float dot = 0.f;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int t = 0; t < kMaxDPerLane; ++t) if (t < nper) dot += a[t] * zc[(size_t)j * D + lane + 32 * t];
-    const float s = wsum(dot) * invT;
-    if (j == pos) spos = s;
-    if (j != self) {
-      const float mn = fmaxf(m, s);
-      l = l * __expf(m - mn) + __expf(s - mn);
-      m = mn;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kSgK) {
+    for (int t = threadIdx.x; t < kSgTile * kSgK; t += 256) {
+      const int r = t / kSgK, kk = t % kSgK;   // A tile: rows m, contiguous in k
+      const int m = m0 + r, k = k0 + kk;
+      sA[kk][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
+      if (b_nt) {
+        const int n = n0 + r;
+        sB[kk][r] = (n < N && k < K) ? B[(size_t)n * K + k] : 0.f;
+      }
     }
+    if (!b_nt) {
+      for (int t = threadIdx.x; t < kSgTile * kSgK; t += 256) {
+        const int kk = t / kSgTile, c = t % kSgTile;   // B tile: rows k, contiguous in n
+        const int k = k0 + kk, n = n0 + c;
+        sB[kk][c] = (n < N && k < K) ? B[(size_t)k * N + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSgK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; bb[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    const float lse = m + __logf(l);
-    lse_out[i] = lse;
-    atomicAdd(loss_out, (lse - spos) / (float)n_r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) C[(size_t)m * N + n] = alpha * acc[i][j];
+    }
   }
 }
 
-// gradient w.r.t. the UN-normalised local rows x_k (z_k = x_k / norm_k):
-//   g_k = gscale/T * [ sum_{j != self(k)} (p_kj + p_jk) z_j - 2 z_pos(k) ],  p_kj = exp(s_kj - lse_k), p_jk = exp(s_kj - lse_j)
-//   dx_k = (g_k - z_k (z_k . g_k)) / norm_k
-// lse_all holds the log-sum-exp of EVERY column-as-row (all-gathered across ranks).
+// per local row i of the logits S [n_r, n_c]: lse over j != self(i), loss += (lse - S[i,pos(i)]) / n_r ; one warp per row
 __global__ void __launch_bounds__(256)
-ntxent_bwd_kernel(const float *__restrict__ zr, const float *__restrict__ norm, int n_r, const float *__restrict__ zc,
-                  const float *__restrict__ lse_all, int n_c, int D, int b_local, int col_offset, int half, float invT,
-                  float gscale, const float *__restrict__ upstream, float *__restrict__ dx) {
-  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (k >= n_r) return;
-  const int nper = D / 32;
-  float a[kMaxDPerLane], g[kMaxDPerLane];
-#pragma unroll
-  for (int t = 0; t < kMaxDPerLane; ++t) { a[t] = t < nper ? zr[(size_t)k * D + lane + 32 * t] : 0.f; g[t] = 0.f; }
+ntxent_rowlse_kernel(const float *__restrict__ S, int n_r, int n_c, int b_local, int col_offset, int half,
+                     float *__restrict__ lse_out, float *__restrict__ loss_out) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n_r) return;
   int self, pos;
-  self_pos(k, b_local, col_offset, half, self, pos);
-  const float lse_k = lse_all[self];
-  for (int j = 0; j < n_c; ++j) {
-    float c[kMaxDPerLane];
-    float dot = 0.f;
+  self_pos(i, b_local, col_offset, half, self, pos);
+  const float *row = S + (size_t)i * n_c;
+  float m = -INFINITY;
+  for (int j = lane; j < n_c; j += 32) if (j != self) m = fmaxf(m, row[j]);
 #pragma unroll
-    for (int t = 0; t < kMaxDPerLane; ++t) {
-      c[t] = t < nper ? zc[(size_t)j * D + lane + 32 * t] : 0.f;
-      dot += a[t] * c[t];
-    }
-    const float s = wsum(dot) * invT;
-    float w = 0.f;
-    if (j != self) w = __expf(s - lse_k) + __expf(s - lse_all[j]);
-    if (j == pos) w -= 2.f;
-#pragma unroll
-    for (int t = 0; t < kMaxDPerLane; ++t) g[t] += w * c[t];
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float l = 0.f;
+  for (int j = lane; j < n_c; j += 32) if (j != self) l += __expf(row[j] - m);
+  l = wsum(l);
+  if (lane == 0) {
+    const float lse = m + __logf(l);
+    lse_out[i] = lse;
+    atomicAdd(loss_out, (lse - row[pos]) / (float)n_r);
   }
-  const float up = upstream ? upstream[0] : 1.f;
-  const float sc = gscale * invT * up;
+}
+
+// in place: S[k,j] <- w_kj = [j != self(k)] (exp(s - lse_k) + exp(s - lse_all[j])) - 2 [j == pos(k)]
+__global__ void __launch_bounds__(256)
+ntxent_weights_kernel(float *__restrict__ S, const float *__restrict__ lse_all, int n_r, int n_c, int b_local,
+                      int col_offset, int half) {
+  const size_t total = (size_t)n_r * n_c;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int k = (int)(e / n_c), j = (int)(e % n_c);
+    int self, pos;
+    self_pos(k, b_local, col_offset, half, self, pos);
+    const float s = S[e];
+    float w = 0.f;
+    if (j != self) w = __expf(s - lse_all[self]) + __expf(s - lse_all[j]);
+    if (j == pos) w -= 2.f;
+    S[e] = w;
+  }
+}
+
+// dx_k = (g_k - z_k (z_k . g_k)) / norm_k with g_k = sc * G[k,:]   (backward of F.normalize); one warp per row
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float *__restrict__ G, const float *__restrict__ z, const float *__restrict__ norm,
+                  float sc, const float *__restrict__ upstream, float *__restrict__ dx, int n, int D) {
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= n) return;
+  const float s = sc * (upstream ? upstream[0] : 1.f);
   float zg = 0.f;
-#pragma unroll
-  for (int t = 0; t < kMaxDPerLane; ++t) { g[t] *= sc; zg += a[t] * g[t]; }
+  for (int d = lane; d < D; d += 32) zg += z[(size_t)k * D + d] * G[(size_t)k * D + d] * s;
   zg = wsum(zg);
   const float inv = 1.f / norm[k];
-#pragma unroll
-  for (int t = 0; t < kMaxDPerLane; ++t)
-    if (t < nper) dx[(size_t)k * D + lane + 32 * t] = (g[t] - a[t] * zg) * inv;
+  for (int d = lane; d < D; d += 32) dx[(size_t)k * D + d] = (G[(size_t)k * D + d] * s - z[(size_t)k * D + d] * zg) * inv;
 }
 
 // fused AdamW (torch.optim.AdamW semantics) over a flat parameter buffer; refreshes the bf16 shadow.
@@ -156,24 +189,31 @@ int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *s
 }
 
 int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local, int col_offset, int half,
-                   float temperature, float *lse_out, float *loss_out, void *stream) {
-  VPF_REQUIRE(zr && zc && lse_out && loss_out, "ntxent_fwd: null pointer");
-  VPF_REQUIRE(D % 32 == 0 && D <= 32 * kMaxDPerLane, "ntxent_fwd: D=%d unsupported (multiple of 32, <= %d)", D, 32 * kMaxDPerLane);
+                   float temperature, float *S_ws, float *lse_out, float *loss_out, void *stream) {
+  VPF_REQUIRE(zr && zc && S_ws && lse_out && loss_out, "ntxent_fwd: null pointer");
   VPF_REQUIRE(n_r == 2 * b_local && n_c == 2 * half && col_offset >= 0 && col_offset + b_local <= half && temperature > 0.f, "ntxent_fwd: inconsistent sizes");
   if (n_r == 0) return VPF_OK;
-  ntxent_fwd_kernel<<<ceil_div(n_r, 8), 256, 0, (cudaStream_t)stream>>>(zr, n_r, zc, n_c, D, b_local, col_offset, half, 1.f / temperature, lse_out, loss_out);
-  return check_launch("ntxent_fwd_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  sgemm_kernel<<<dim3(ceil_div(n_c, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(zr, zc, S_ws, n_r, n_c, D, 1.f / temperature, 1);
+  VPF_TRY(check_launch("sgemm_kernel"));
+  ntxent_rowlse_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(S_ws, n_r, n_c, b_local, col_offset, half, lse_out, loss_out);
+  return check_launch("ntxent_rowlse_kernel");
 }
 
 int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all, int n_c, int D,
                    int b_local, int col_offset, int half, float temperature, float gscale, const float *upstream,
-                   float *dx, void *stream) {
-  VPF_REQUIRE(zr && norm && zc && lse_all && dx, "ntxent_bwd: null pointer");
-  VPF_REQUIRE(D % 32 == 0 && D <= 32 * kMaxDPerLane, "ntxent_bwd: D=%d unsupported", D);
+                   float *S_ws, float *G_ws, float *dx, void *stream) {
+  VPF_REQUIRE(zr && norm && zc && lse_all && S_ws && G_ws && dx, "ntxent_bwd: null pointer");
   VPF_REQUIRE(n_r == 2 * b_local && n_c == 2 * half && col_offset >= 0 && col_offset + b_local <= half && temperature > 0.f, "ntxent_bwd: inconsistent sizes");
   if (n_r == 0) return VPF_OK;
-  ntxent_bwd_kernel<<<ceil_div(n_r, 8), 256, 0, (cudaStream_t)stream>>>(zr, norm, n_r, zc, lse_all, n_c, D, b_local, col_offset, half, 1.f / temperature, gscale, upstream, dx);
-  return check_launch("ntxent_bwd_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)n_r * n_c;
+  ntxent_weights_kernel<<<(int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)), 256, 0, st>>>(S_ws, lse_all, n_r, n_c, b_local, col_offset, half);
+  VPF_TRY(check_launch("ntxent_weights_kernel"));
+  sgemm_kernel<<<dim3(ceil_div(D, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(S_ws, zc, G_ws, n_r, D, n_c, 1.f, 0);
+  VPF_TRY(check_launch("sgemm_kernel"));
+  l2norm_bwd_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(G_ws, zr, norm, gscale / temperature, upstream, dx, n_r, D);
+  return check_launch("l2norm_bwd_kernel");
 }
 
 int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n, const float *lr_ptr,

@@ -1,8 +1,8 @@
 """NT-Xent contrastive objective: drop-in for `lightly.loss.NTXentLoss(temperature)` as used at pretrain.py:155,196,202,
 plus the fused loss composition of pretrain.py:189-207.
 
-Fused kernels (csrc/loss_optim.cu): row normalisation, similarity + online log-sum-exp + reduction (the [2b,2b]
-logits are never materialised), and a single backward kernel.  With gather_distributed=True the columns are the
+Kernels (csrc/loss_optim.cu): row normalisation, fp32 similarity GEMM into a small logits scratch ([2b, 2bW]; 1 MB
+at b = 256), masked row log-sum-exp + reduction; backward = weights in place, fp32 GEMM, normalisation backward.  With gather_distributed=True the columns are the
 all-gathered embeddings of every rank (NCCL all-gather of the L2-normalised rows; the backward needs only an
 all-gather of the per-row log-sum-exp vector) so negatives span the global batch.
 """
@@ -62,12 +62,12 @@ class _NTXentCore:
         else:
             zc, col_offset, half = z, 0, b
         loss = ops.zeros_(torch.empty(1, dtype=F32, device=x.device))
-        lse = ops.ntxent_fwd(z, zc, b, col_offset, half, temperature, loss)
-        return loss, (z, norm, zc, lse, b, col_offset, half, temperature, dist)
+        lse, S = ops.ntxent_fwd(z, zc, b, col_offset, half, temperature, loss)
+        return loss, (z, norm, zc, lse, b, col_offset, half, temperature, dist, S)
 
     @staticmethod
     def bwd(saved, gscale, upstream=None):
-        z, norm, zc, lse, b, col_offset, half, temperature, dist = saved
+        z, norm, zc, lse, b, col_offset, half, temperature, dist, S = saved
         if dist is not None:
             lse_all = torch.empty(2 * half, dtype=F32, device=z.device)
             dist.all_gather_into_tensor(lse_all[:half], lse[:b].contiguous())
@@ -75,7 +75,7 @@ class _NTXentCore:
         else:
             lse_all = lse
         # DDP averages parameter gradients over ranks, so the per-rank seed stays 1/(2b) for any world size
-        return ops.ntxent_bwd(z, norm, zc, lse_all, b, col_offset, half, temperature, gscale / (2 * b), upstream)
+        return ops.ntxent_bwd(z, norm, zc, lse_all, S, b, col_offset, half, temperature, gscale / (2 * b), upstream)
 
 
 class _NTXentFn(torch.autograd.Function):

@@ -288,18 +288,21 @@ def l2norm_rows(x):
 
 
 def ntxent_fwd(zr, zc, b_local, col_offset, half, temperature, loss_out):
+    """-> (lse [n_r], logits scratch S [n_r, n_c] to hand to ntxent_bwd)."""
     n_r, D = zr.shape
     lse = torch.empty(n_r, dtype=F32, device=zr.device)
+    S = torch.empty((n_r, zc.shape[0]), dtype=F32, device=zr.device)
     _lib.call("vpf_ntxent_fwd", _p(zr), _i(n_r), _p(zc), _i(zc.shape[0]), _i(D), _i(b_local), _i(col_offset), _i(half),
-              _f(temperature), _p(lse), _p(loss_out), _s())
-    return lse
+              _f(temperature), _p(S), _p(lse), _p(loss_out), _s())
+    return lse, S
 
 
-def ntxent_bwd(zr, norm, zc, lse_all, b_local, col_offset, half, temperature, gscale, upstream=None):
+def ntxent_bwd(zr, norm, zc, lse_all, S, b_local, col_offset, half, temperature, gscale, upstream=None):
     n_r, D = zr.shape
     dx = torch.empty((n_r, D), dtype=F32, device=zr.device)
+    G = torch.empty((n_r, D), dtype=F32, device=zr.device)
     _lib.call("vpf_ntxent_bwd", _p(zr), _p(norm), _i(n_r), _p(zc), _p(lse_all), _i(zc.shape[0]), _i(D), _i(b_local),
-              _i(col_offset), _i(half), _f(temperature), _f(gscale), _p(upstream), _p(dx), _s())
+              _i(col_offset), _i(half), _f(temperature), _f(gscale), _p(upstream), _p(S), _p(G), _p(dx), _s())
     return dx
 
 
