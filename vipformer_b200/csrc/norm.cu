@@ -23,9 +23,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// 4-wide accessors: lane l owns elements [(l + 32 v) * 4, +4) of a row  (16-byte fp32 / 8-byte bf16 accesses)
+template <typename T> __device__ __forceinline__ float4 ld4(const T *p, size_t i);
+template <> __device__ __forceinline__ float4 ld4<float>(const float *p, size_t i) { return *reinterpret_cast<const float4 *>(p + i); }
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16 *p, size_t i) {
+  const uint2 u = *reinterpret_cast<const uint2 *>(p + i);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void st4(T *p, size_t i, float4 v);
+template <> __device__ __forceinline__ void st4<float>(float *p, size_t i, float4 v) { *reinterpret_cast<float4 *>(p + i) = v; }
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, size_t i, float4 v) {
+  uint2 u;
+  *reinterpret_cast<__nv_bfloat162 *>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162 *>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2 *>(p + i) = u;
+}
+
 // ------------------------------------------------------------- LayerNorm fwd
-// one warp per row; NPER = D/32 values per lane held in registers
-template <typename Tin, int NPER>
+// one warp per row; NPER = D/32 values per lane held in registers.  VEC: lane owns float4 groups (D % 128 == 0).
+template <typename Tin, int NPER, bool VEC>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
               const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
@@ -35,37 +53,61 @@ ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_
   if (row >= T) return;
   float v[NPER];
   float s = 0.f;
+  if constexpr (VEC) {
 #pragma unroll
-  for (int i = 0; i < NPER; ++i) {
-    const int c = lane + 32 * i;
-    float t = ldf<Tin>(x, (size_t)row * D + c);
-    if (add) t += add[(size_t)(row % add_rows) * D + c];
-    v[i] = t;
-    s += t;
-  }
-  if (xsum) {
+    for (int q = 0; q < NPER / 4; ++q) {
+      const int c = (lane + 32 * q) * 4;
+      float4 t = ld4<Tin>(x, (size_t)row * D + c);
+      if (add) {
+        const float4 a = ld4<float>(add, (size_t)(row % add_rows) * D + c);
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+      }
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      s += (t.x + t.y) + (t.z + t.w);
+      if (xsum) st4<float>(xsum, (size_t)row * D + c, t);
+    }
+  } else {
 #pragma unroll
-    for (int i = 0; i < NPER; ++i) xsum[(size_t)row * D + lane + 32 * i] = v[i];
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float t = ldf<Tin>(x, (size_t)row * D + c);
+      if (add) t += add[(size_t)(row % add_rows) * D + c];
+      v[i] = t;
+      s += t;
+      if (xsum) xsum[(size_t)row * D + c] = t;
+    }
   }
   const float mean = warp_sum(s) * (1.f / D);
-  float q = 0.f;
+  float q2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q2 += d * d; }
+  const float rstd = rsqrtf(warp_sum(q2) * (1.f / D) + eps);
   if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
+  if constexpr (VEC) {
 #pragma unroll
-  for (int i = 0; i < NPER; ++i) {
-    const int c = lane + 32 * i;
-    float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-    if (relu) o = fmaxf(o, 0.f);
-    y[(size_t)row * D + c] = __float2bfloat16(o);
+    for (int q = 0; q < NPER / 4; ++q) {
+      const int c = (lane + 32 * q) * 4;
+      const float4 g = ld4<float>(gamma, c), b = ld4<float>(beta, c);
+      float4 o = make_float4((v[4 * q] - mean) * rstd * g.x + b.x, (v[4 * q + 1] - mean) * rstd * g.y + b.y,
+                             (v[4 * q + 2] - mean) * rstd * g.z + b.z, (v[4 * q + 3] - mean) * rstd * g.w + b.w);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4<__nv_bfloat16>(y, (size_t)row * D + c, o);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (relu) o = fmaxf(o, 0.f);
+      y[(size_t)row * D + c] = __float2bfloat16(o);
+    }
   }
 }
 
 // ------------------------------------------------------------- LayerNorm bwd
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = gamma * dy  (dy masked by y > 0 when relu)
 // dx_out = dres + dx;  dpos[row % pos_rows] += dx_out;  dgamma += sum dy*xhat;  dbeta += sum dy
-template <typename Tdy, typename Tx, typename Tdx, int NPER>
+template <typename Tdy, typename Tx, typename Tdx, int NPER, bool VEC>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_bfloat16 *__restrict__ y_relu,
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in, const float *__restrict__ gamma,
@@ -74,38 +116,89 @@ ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_b
   constexpr int D = NPER * 32;
   __shared__ float s_dg[D], s_db[D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float dg[NPER], db[NPER];
+  float dg[NPER], db[NPER], gm[NPER];
+  // element i of this lane lives at column col(i)
+  auto col = [&](int i) { return VEC ? (lane + 32 * (i >> 2)) * 4 + (i & 3) : lane + 32 * i; };
 #pragma unroll
-  for (int i = 0; i < NPER; ++i) dg[i] = db[i] = 0.f;
+  for (int i = 0; i < NPER; ++i) { dg[i] = db[i] = 0.f; gm[i] = gamma[col(i)]; }
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(T, row0 + rows_per_cta);
   for (int row = row0 + warp; row < row1; row += 8) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float g[NPER], xh[NPER];
+    const size_t base = (size_t)row * D;
+    float d[NPER], xh[NPER], rsd[NPER];
+    if constexpr (VEC) {
+#pragma unroll
+      for (int q = 0; q < NPER / 4; ++q) {
+        const int c = (lane + 32 * q) * 4;
+        const float4 a = ld4<Tdy>(dy, base + c), b = ld4<Tx>(x, base + c);
+        d[4 * q] = a.x; d[4 * q + 1] = a.y; d[4 * q + 2] = a.z; d[4 * q + 3] = a.w;
+        xh[4 * q] = b.x; xh[4 * q + 1] = b.y; xh[4 * q + 2] = b.z; xh[4 * q + 3] = b.w;
+        if (dres) {
+          const float4 r = ld4<float>(dres, base + c);
+          rsd[4 * q] = r.x; rsd[4 * q + 1] = r.y; rsd[4 * q + 2] = r.z; rsd[4 * q + 3] = r.w;
+        }
+        if (y_relu) {
+          const float4 yy = ld4<__nv_bfloat16>(y_relu, base + c);
+          if (!(yy.x > 0.f)) d[4 * q] = 0.f;
+          if (!(yy.y > 0.f)) d[4 * q + 1] = 0.f;
+          if (!(yy.z > 0.f)) d[4 * q + 2] = 0.f;
+          if (!(yy.w > 0.f)) d[4 * q + 3] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int c = lane + 32 * i;
+        d[i] = ldf<Tdy>(dy, base + c);
+        if (y_relu && !(__bfloat162float(y_relu[base + c]) > 0.f)) d[i] = 0.f;
+        xh[i] = ldf<Tx>(x, base + c);
+        if (dres) rsd[i] = dres[base + c];
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NPER; ++i) {
-      const int c = lane + 32 * i;
-      float d = ldf<Tdy>(dy, (size_t)row * D + c);
-      if (y_relu && !(__bfloat162float(y_relu[(size_t)row * D + c]) > 0.f)) d = 0.f;
-      xh[i] = (ldf<Tx>(x, (size_t)row * D + c) - mean) * rstd;
-      dg[i] += d * xh[i];
-      db[i] += d;
-      g[i] = d * gamma[c];
-      s1 += g[i];
-      s2 += g[i] * xh[i];
+      xh[i] = (xh[i] - mean) * rstd;
+      dg[i] += d[i] * xh[i];
+      db[i] += d[i];
+      d[i] *= gm[i];
+      s1 += d[i];
+      s2 += d[i] * xh[i];
     }
     s1 = warp_sum(s1) * (1.f / D);
     s2 = warp_sum(s2) * (1.f / D);
 #pragma unroll
     for (int i = 0; i < NPER; ++i) {
-      const int c = lane + 32 * i;
-      float o = rstd * (g[i] - s1 - xh[i] * s2);
-      if (dres) o += dres[(size_t)row * D + c];
-      stf<Tdx>(dx, (size_t)row * D + c, o);
-      if (dpos) {
-        if (pos_rows >= T) dpos[(size_t)row * D + c] += o;
-        else atomicAdd(dpos + (size_t)(row % pos_rows) * D + c, o);
+      d[i] = rstd * (d[i] - s1 - xh[i] * s2);
+      if (dres) d[i] += rsd[i];
+    }
+    if constexpr (VEC) {
+#pragma unroll
+      for (int q = 0; q < NPER / 4; ++q) {
+        const int c = (lane + 32 * q) * 4;
+        const float4 o = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+        st4<Tdx>(dx, base + c, o);
+        if (dpos) {
+          if (pos_rows >= T) {
+            float4 pp = ld4<float>(dpos, base + c);
+            pp.x += o.x; pp.y += o.y; pp.z += o.z; pp.w += o.w;
+            st4<float>(dpos, base + c, pp);
+          } else {
+            float *pp = dpos + (size_t)(row % pos_rows) * D + c;
+            atomicAdd(pp, o.x); atomicAdd(pp + 1, o.y); atomicAdd(pp + 2, o.z); atomicAdd(pp + 3, o.w);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int c = lane + 32 * i;
+        stf<Tdx>(dx, base + c, d[i]);
+        if (dpos) {
+          if (pos_rows >= T) dpos[base + c] += d[i];
+          else atomicAdd(dpos + (size_t)(row % pos_rows) * D + c, d[i]);
+        }
       }
     }
   }
@@ -113,7 +206,7 @@ ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_b
     for (int c = threadIdx.x; c < D; c += 256) { s_dg[c] = 0.f; s_db[c] = 0.f; }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NPER; ++i) { atomicAdd(&s_dg[lane + 32 * i], dg[i]); atomicAdd(&s_db[lane + 32 * i], db[i]); }
+    for (int i = 0; i < NPER; ++i) { atomicAdd(&s_dg[col(i)], dg[i]); atomicAdd(&s_db[col(i)], db[i]); }
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += 256) {
       atomicAdd(dgamma + c, s_dg[c]);
@@ -544,9 +637,9 @@ typedef __nv_bfloat16 bf16;
 
 #define LN_DISPATCH(D, MACRO)                                                                       \
   switch (D) {                                                                                      \
-    case 64: MACRO(2); break; case 128: MACRO(4); break; case 256: MACRO(8); break;                 \
-    case 384: MACRO(12); break; case 512: MACRO(16); break; case 768: MACRO(24); break;             \
-    case 1024: MACRO(32); break;                                                                    \
+    case 64: MACRO(2, false); break; case 128: MACRO(4, true); break; case 256: MACRO(8, true); break; \
+    case 384: MACRO(12, true); break; case 512: MACRO(16, true); break; case 768: MACRO(24, true); break; \
+    case 1024: MACRO(32, true); break;                                                              \
     default: return fail(VPF_EINVAL, "layernorm: D=%d unsupported (64,128,256,384,512,768,1024)", D); \
   }
 
@@ -560,9 +653,9 @@ int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows,
   if (T == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(T, 8);
-#define LNF(NP)                                                                                                     \
-  if (x_bf16) ln_fwd_kernel<bf16, NP><<<grid, 256, 0, st>>>((const bf16 *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
-  else ln_fwd_kernel<float, NP><<<grid, 256, 0, st>>>((const float *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu)
+#define LNF(NP, VEC)                                                                                                \
+  if (x_bf16) ln_fwd_kernel<bf16, NP, VEC><<<grid, 256, 0, st>>>((const bf16 *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
+  else ln_fwd_kernel<float, NP, VEC><<<grid, 256, 0, st>>>((const float *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu)
   LN_DISPATCH(D, LNF)
 #undef LNF
   return check_launch("ln_fwd_kernel");
@@ -577,15 +670,15 @@ int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, co
   cudaStream_t st = (cudaStream_t)stream;
   const int rows_per_cta = max(8, ceil_div(T, num_sms() * 4));
   const int grid = ceil_div(T, rows_per_cta);
-#define LNB_CALL(TDY, TX, TDX, NP)                                                                                    \
-  ln_bwd_kernel<TDY, TX, TDX, NP><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
+#define LNB_CALL(TDY, TX, TDX, NP, VEC)                                                                               \
+  ln_bwd_kernel<TDY, TX, TDX, NP, VEC><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
                                                          (TDX *)dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta)
-#define LNB(NP)                                                                     \
-  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP);                 \
-  else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP);          \
-  else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP);      \
-  else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP);        \
-  else if (dy_bf16 && x_bf16 && !dx_bf16) LNB_CALL(bf16, bf16, float, NP);          \
+#define LNB(NP, VEC)                                                                     \
+  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP, VEC);                 \
+  else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP, VEC);          \
+  else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP, VEC);      \
+  else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP, VEC);        \
+  else if (dy_bf16 && x_bf16 && !dx_bf16) LNB_CALL(bf16, bf16, float, NP, VEC);          \
   else return fail(VPF_EINVAL, "layernorm_bwd: unsupported dtype combination dy_bf16=%d x_bf16=%d dx_bf16=%d", dy_bf16, x_bf16, dx_bf16)
   LN_DISPATCH(D, LNB)
 #undef LNB
