@@ -481,6 +481,156 @@ attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__
   }
 }
 
+// ------------------------------------------- backward, fused (Lq <= 128): dQ, dK, dV in ONE pass
+// One CTA (8 warps) per (sample, head) holds all queries.  Per 64-key tile:
+//   phase 1 (warp = 16 query rows):  S = Q K^T, P = exp2(S - lse), dP = dO V^T, dS = P (dP - delta) scale;
+//                                    dQ += dS K (registers); dropped P and dS go to shared memory as bf16 tiles
+//   phase 2 (warp = 16 keys x 32 d): dV = P^T dO, dK = dS^T Q with the A operand read TRANSPOSED (ldmatrix.trans)
+// so S / P / dP / dS and the dropout mask are computed once (the two-kernel path computes them twice: 5 GEMMs vs 7).
+__global__ void __launch_bounds__(256)
+attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
+                      int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
+                      const float *__restrict__ delta, bf16 *__restrict__ dQ, int lddq, bf16 *__restrict__ dK,
+                      bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, float scale, float drop_p,
+                      const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  bf16 *sQ = reinterpret_cast<bf16 *>(attn_smem);   // [128][64]
+  bf16 *sdO = sQ + 128 * HD;                        // [128][64]
+  bf16 *sK = sdO + 128 * HD;                        // [2][64][64]
+  bf16 *sV = sK + 2 * 64 * HD;                      // [2][64][64]
+  bf16 *sP = sV + 2 * 64 * HD;                      // [128 q][64 keys]  dropped probabilities
+  bf16 *sdS = sP + 128 * 64;                        // [128 q][64 keys]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
+  const float sc2 = scale * kLog2e;
+  const bf16 *Kb = K + (size_t)b * Lk * ldkv + h * HD, *Vb = V + (size_t)b * Lk * ldkv + h * HD;
+
+  load_tile_async(sQ, Q + (size_t)b * Lq * ldq + h * HD, ldq, Lq, 128, tid, 256);
+  load_tile_async(sdO, dO + (size_t)b * Lq * lddo + h * HD, lddo, Lq, 128, tid, 256);
+  load_tile_async(sK, Kb, ldkv, Lk, 64, tid, 256);
+  load_tile_async(sV, Vb, ldkv, Lk, 64, tid, 256);
+  cp_async_commit();
+
+  uint32_t qa[4][4], da[4][4];
+  const int r0 = warp * 16 + (lane >> 2);   // this thread's first query row (second is +8)
+  float lse[2], dl[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = r0 + q * 8;
+    lse[q] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
+    dl[q] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+  }
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const int kb = (warp & 3) * 16, dh = (warp >> 2) * 32;   // phase-2 ownership: 16 keys x 32 head-dim columns
+  const int m = lane >> 3, rr = lane & 7;
+  const int nt = (Lk + 63) / 64;
+
+  for (int t = 0; t < nt; ++t) {
+    const int k0 = t * 64;
+    if (t + 1 < nt) {
+      load_tile_async(sK + ((t + 1) & 1) * 64 * HD, Kb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, 256);
+      load_tile_async(sV + ((t + 1) & 1) * 64 * HD, Vb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, 256);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();   // tile t landed; phase 2 of tile t-1 is finished with sP / sdS
+    if (t == 0) {
+      load_a_frags(qa, sQ, warp * 16, lane);
+      load_a_frags(da, sdO, warp * 16, lane);
+    }
+    const bf16 *tK = sK + (t & 1) * 64 * HD, *tV = sV + (t & 1) * 64 * HD;
+    {
+      // ---------------- phase 1
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      mma_a_tileT(s, qa, tK, lane);    // S = Q K^T
+      mma_a_tileT(dp, da, tV, lane);   // dP = dO V^T
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const int je = k0 + nb * 8 + (lane & 3) * 2;   // even key: (je, je+1) share a dropout hash
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int i = r0 + q * 8;
+          uint32_t hsh = 0;
+          if (dc.thr) hsh = block_hash(dc, bh, i, je, Lq, Lk);
+          float pd[2], ds[2];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int e = q * 2 + w, j = je + w;
+            const float p = j < Lk ? exp2f(s[nb][e] * sc2 - lse[q]) : 0.f;
+            float dpe = dp[nb][e];
+            pd[w] = p;
+            if (dc.thr) {
+              const bool keep = keep_from(hsh, i, j, dc.thr);
+              pd[w] = keep ? p * dc.scale : 0.f;
+              dpe = keep ? dpe * dc.scale : 0.f;
+            }
+            ds[w] = p * (dpe - dl[q]) * scale;
+            s[nb][e] = ds[w];
+          }
+          const uint32_t off = tile_off(warp * 16 + (lane >> 2) + q * 8, nb) + (lane & 3) * 4;
+          *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(sP) + off) = pack_bf16(pd[0], pd[1]);
+          *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(sdS) + off) = pack_bf16(ds[0], ds[1]);
+        }
+      }
+      uint32_t pa[4][4];
+      pack_p(pa, s);
+      mma_p_tile(dq, pa, tK, lane);    // dQ += dS K
+    }
+    __syncthreads();   // sP / sdS complete
+    {
+      // ---------------- phase 2: dV[kb..+16][dh..+32] = P^T dO, dK = dS^T Q  (k dimension = the 128 queries)
+      float dv[4][4], dk[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        uint32_t ap[4], as[4];
+        const uint32_t aoff = tile_off(16 * kk + (m >> 1) * 8 + rr, kb / 8 + (m & 1));
+        ldsm4t(ap, smem_addr(sP) + aoff);
+        ldsm4t(as, smem_addr(sdS) + aoff);
+#pragma unroll
+        for (int nd = 0; nd < 4; nd += 2) {
+          uint32_t bo[4], bq[4];
+          const uint32_t boff = tile_off(16 * kk + (m & 1) * 8 + rr, dh / 8 + nd + (m >> 1));
+          ldsm4t(bo, smem_addr(sdO) + boff);
+          ldsm4t(bq, smem_addr(sQ) + boff);
+          mma16816(dv[nd], ap, bo[0], bo[1]);
+          mma16816(dv[nd + 1], ap, bo[2], bo[3]);
+          mma16816(dk[nd], as, bq[0], bq[1]);
+          mma16816(dk[nd + 1], as, bq[2], bq[3]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = k0 + kb + (lane >> 2) + q * 8;
+        if (j < Lk) {
+          bf16 *pk = dK + ((size_t)b * Lk + j) * lddkv + h * HD + dh + (lane & 3) * 2;
+          bf16 *pv = dV + ((size_t)b * Lk + j) * lddkv + h * HD + dh + (lane & 3) * 2;
+#pragma unroll
+          for (int nd = 0; nd < 4; ++nd) {
+            *reinterpret_cast<uint32_t *>(pk + nd * 8) = pack_bf16(dk[nd][2 * q], dk[nd][2 * q + 1]);
+            *reinterpret_cast<uint32_t *>(pv + nd * 8) = pack_bf16(dv[nd][2 * q], dv[nd][2 * q + 1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = r0 + q * 8;
+    if (i < Lq) {
+      bf16 *pq = dQ + ((size_t)b * Lq + i) * lddq + h * HD + (lane & 3) * 2;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t *>(pq + nd * 8) = pack_bf16(dq[nd][2 * q], dq[nd][2 * q + 1]);
+    }
+  }
+}
+
 // rows per CTA: 128 (8 warps) when that pads no more than 64-row tiles would, else 64 (4 warps)
 static inline bool use8(int L) { return ceil_div(L, 128) * 128 <= ceil_div(L, 64) * 64; }
 template <typename Kern> static int set_smem(Kern k, int bytes) {
@@ -528,6 +678,13 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   const long long total = (long long)B * Lq * H;
   attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
   VPF_TRY(check_launch("attn_delta_kernel"));
+  if (Lq <= 128) {
+    const int smem = (2 * 128 + 4 * 64 + 2 * 128) * HD * 2;
+    VPF_TRY(set_smem(attn_bwd_fused_kernel, smem));
+    attn_bwd_fused_kernel<<<B * H, 256, smem, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
+                                                     (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+    return check_launch("attn_bwd_fused_kernel");
+  }
 #define DKV_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
 #define DQ_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (use8(Lk)) {
