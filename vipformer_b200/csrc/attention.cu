@@ -487,29 +487,31 @@ attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__
 //                                    dQ += dS K (registers); dropped P and dS go to shared memory as bf16 tiles
 //   phase 2 (warp = 16 keys x 32 d): dV = P^T dO, dK = dS^T Q with the A operand read TRANSPOSED (ldmatrix.trans)
 // so S / P / dP / dS and the dropout mask are computed once (the two-kernel path computes them twice: 5 GEMMs vs 7).
-__global__ void __launch_bounds__(256)
+template <int NQW>
+__global__ void __launch_bounds__(32 * NQW)
 attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
                       int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
                       const float *__restrict__ delta, bf16 *__restrict__ dQ, int lddq, bf16 *__restrict__ dK,
                       bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, float scale, float drop_p,
                       const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
   extern __shared__ __align__(128) uint8_t attn_smem[];
-  bf16 *sQ = reinterpret_cast<bf16 *>(attn_smem);   // [128][64]
-  bf16 *sdO = sQ + 128 * HD;                        // [128][64]
-  bf16 *sK = sdO + 128 * HD;                        // [2][64][64]
+  constexpr int TQ = 16 * NQW, NT_ = 32 * NQW;
+  bf16 *sQ = reinterpret_cast<bf16 *>(attn_smem);   // [TQ][64]
+  bf16 *sdO = sQ + TQ * HD;                         // [TQ][64]
+  bf16 *sK = sdO + TQ * HD;                         // [2][64][64]
   bf16 *sV = sK + 2 * 64 * HD;                      // [2][64][64]
-  bf16 *sP = sV + 2 * 64 * HD;                      // [128 q][64 keys]  dropped probabilities
-  bf16 *sdS = sP + 128 * 64;                        // [128 q][64 keys]
+  bf16 *sP = sV + 2 * 64 * HD;                      // [TQ q][64 keys]  dropped probabilities
+  bf16 *sdS = sP + TQ * 64;                         // [TQ q][64 keys]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const DropCfg dc = make_drop(drop_p, seed_ptr, op_id);
   const float sc2 = scale * kLog2e;
   const bf16 *Kb = K + (size_t)b * Lk * ldkv + h * HD, *Vb = V + (size_t)b * Lk * ldkv + h * HD;
 
-  load_tile_async(sQ, Q + (size_t)b * Lq * ldq + h * HD, ldq, Lq, 128, tid, 256);
-  load_tile_async(sdO, dO + (size_t)b * Lq * lddo + h * HD, lddo, Lq, 128, tid, 256);
-  load_tile_async(sK, Kb, ldkv, Lk, 64, tid, 256);
-  load_tile_async(sV, Vb, ldkv, Lk, 64, tid, 256);
+  load_tile_async(sQ, Q + (size_t)b * Lq * ldq + h * HD, ldq, Lq, TQ, tid, NT_);
+  load_tile_async(sdO, dO + (size_t)b * Lq * lddo + h * HD, lddo, Lq, TQ, tid, NT_);
+  load_tile_async(sK, Kb, ldkv, Lk, 64, tid, NT_);
+  load_tile_async(sV, Vb, ldkv, Lk, 64, tid, NT_);
   cp_async_commit();
 
   uint32_t qa[4][4], da[4][4];
@@ -531,8 +533,8 @@ attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restric
   for (int t = 0; t < nt; ++t) {
     const int k0 = t * 64;
     if (t + 1 < nt) {
-      load_tile_async(sK + ((t + 1) & 1) * 64 * HD, Kb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, 256);
-      load_tile_async(sV + ((t + 1) & 1) * 64 * HD, Vb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, 256);
+      load_tile_async(sK + ((t + 1) & 1) * 64 * HD, Kb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT_);
+      load_tile_async(sV + ((t + 1) & 1) * 64 * HD, Vb + (size_t)(k0 + 64) * ldkv, ldkv, Lk - k0 - 64, 64, tid, NT_);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -582,13 +584,13 @@ attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restric
       mma_p_tile(dq, pa, tK, lane);    // dQ += dS K
     }
     __syncthreads();   // sP / sdS complete
-    {
-      // ---------------- phase 2: dV[kb..+16][dh..+32] = P^T dO, dK = dS^T Q  (k dimension = the 128 queries)
+    if (warp < 8) {
+      // ---------------- phase 2: dV[kb..+16][dh..+32] = P^T dO, dK = dS^T Q  (k dimension = the TQ queries)
       float dv[4][4], dk[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
+      for (int kk = 0; kk < NQW; ++kk) {
         uint32_t ap[4], as[4];
         const uint32_t aoff = tile_off(16 * kk + (m >> 1) * 8 + rr, kb / 8 + (m & 1));
         ldsm4t(ap, smem_addr(sP) + aoff);
@@ -678,13 +680,20 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   const long long total = (long long)B * Lq * H;
   attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
   VPF_TRY(check_launch("attn_delta_kernel"));
+#define FUSED_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (Lq <= 128) {
-    const int smem = (2 * 128 + 4 * 64 + 2 * 128) * HD * 2;
-    VPF_TRY(set_smem(attn_bwd_fused_kernel, smem));
-    attn_bwd_fused_kernel<<<B * H, 256, smem, st>>>((const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws,
-                                                     (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
-    return check_launch("attn_bwd_fused_kernel");
+    const int smem = (4 * 128 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_bwd_fused_kernel<8>, smem));
+    attn_bwd_fused_kernel<8><<<B * H, 256, smem, st>>>(FUSED_ARGS);
+    return check_launch("attn_bwd_fused_kernel<8>");
   }
+  if (Lq <= 160) {   // image branch: 144 tokens
+    const int smem = (4 * 160 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_bwd_fused_kernel<10>, smem));
+    attn_bwd_fused_kernel<10><<<B * H, 320, smem, st>>>(FUSED_ARGS);
+    return check_launch("attn_bwd_fused_kernel<10>");
+  }
+#undef FUSED_ARGS
 #define DKV_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
 #define DQ_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (use8(Lk)) {
