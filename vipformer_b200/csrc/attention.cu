@@ -654,7 +654,12 @@ int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE(Lq >= 1 && Lk >= 1 && H >= 1 && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0, "attention_fwd: bad shape/stride");
   VPF_REQUIRE((long long)B * H <= 65535 * 1LL * 65535, "attention_fwd: too many heads");
   if (B == 0) return VPF_OK;
-  if (use8(Lq)) {
+  if (Lq > 128 && Lq <= 160) {   // image branch (144 tokens): all queries in one 10-warp CTA, K/V streamed once
+    const int smem = (160 + 4 * 64) * HD * 2;
+    VPF_TRY(set_smem(attn_fwd_kernel<10>, smem));
+    attn_fwd_kernel<10><<<dim3(1, B * H), 320, smem, (cudaStream_t)stream>>>(
+        (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (bf16 *)O, ldo, LSE, H, Lq, Lk, scale, drop_p, seed_ptr, op_id);
+  } else if (use8(Lq)) {
     const int smem = (128 + 4 * 64) * HD * 2;
     VPF_TRY(set_smem(attn_fwd_kernel<8>, smem));
     attn_fwd_kernel<8><<<dim3(ceil_div(Lq, 128), B * H), 256, smem, (cudaStream_t)stream>>>(
