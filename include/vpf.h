@@ -137,6 +137,11 @@ typedef struct vpf_gemm_epilogue {
   float *gm_out_f32;
   void *gm_out_bf16;
   unsigned char *gm_argmax;
+  /* gm_cols = 1: the patch runs along the COLUMNS of C (call the GEMM transposed: A = weights [channels, K],
+   * B = activations [points, K]); a thread then owns one channel and 32 consecutive points, the pool is pure
+   * register work and gm_out_*[(col / S) * gm_ld + row] is written coalesced.  row_bias [M] is added after the max. */
+  int gm_cols;
+  const float *row_bias;
 } vpf_gemm_epilogue;
 
 int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb,

@@ -154,3 +154,23 @@ def test_gemm_group_max_epilogue(S, store):
     picked = acc.view(G, S, N).gather(1, am.long()[:, None]).squeeze(1)
     assert (ref - picked).abs().max().item() <= 2e-3 * ref.abs().max().item()
     assert (am.long() == ri).float().mean().item() > 0.995
+
+
+@pytest.mark.parametrize("S", [8, 32])
+def test_gemm_group_max_transposed(S):
+    """Pool-only epilogue with the patch along the columns (the GEMM is called as C^T = W . X^T)."""
+    from vipformer_b200 import ops
+
+    G, C, K = 301, 256, 192
+    R = G * S
+    X, W = _mk((R, K), 14), _mk((C, K), 15)
+    bias = torch.randn(C, device="cuda")
+    acc = X.float() @ W.float().t() + bias
+    gm_f = torch.empty((G, C), device="cuda")
+    am = torch.empty((G, C), device="cuda", dtype=torch.uint8)
+    ops.gemm(W, X, None, row_bias=bias, gm_S=S, gm_f32=gm_f, gm_argmax=am, gm_cols=True)
+    ref, ri = acc.view(G, S, C).max(1)
+    _close(gm_f, ref, False)
+    picked = acc.view(G, S, C).gather(1, am.long()[:, None]).squeeze(1)
+    assert (ref - picked).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert (am.long() == ri).float().mean().item() > 0.995

@@ -46,6 +46,7 @@ struct GemmArgs {
   int a_mn, b_mn;
   int num_m_tiles, num_n_tiles, kblocks, kblocks_per_split, splits;
   int tma_epi;   // 1: TMA epilogue (aligned outputs); 0: generic direct-global epilogue
+  int m_fast;    // 1: consecutive work items walk the M tiles first (they share the B tile), else the N tiles first
   vpf_gemm_epilogue e;
 };
 
@@ -115,10 +116,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int n_tile = w % g.num_n_tiles;
-      const int t = w / g.num_n_tiles;
-      const int m_tile = t % g.num_m_tiles;
-      const int split = t / g.num_m_tiles;
+      const int tiles = g.num_m_tiles * g.num_n_tiles;
+      const int split = w / tiles, wt = w % tiles;
+      const int n_tile = g.m_fast ? wt / g.num_m_tiles : wt % g.num_n_tiles;
+      const int m_tile = g.m_fast ? wt % g.num_m_tiles : wt / g.num_n_tiles;
       const int kb0 = split * g.kblocks_per_split, kb1 = min(kb0 + g.kblocks_per_split, g.kblocks);
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -153,7 +154,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t phase = 0;
     int iter = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++iter) {
-      const int split = (w / g.num_n_tiles) / g.num_m_tiles;
+      const int split = w / (g.num_m_tiles * g.num_n_tiles);
       const int kb0 = split * g.kblocks_per_split, kb1 = min(kb0 + g.kblocks_per_split, g.kblocks);
       const int acc = iter & 1;
       ptx::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
@@ -205,8 +206,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int iter = 0;
     uint32_t ld_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++iter) {
-      const int n_tile = w % g.num_n_tiles;
-      const int m_tile = (w / g.num_n_tiles) % g.num_m_tiles;
+      const int wt = w % (g.num_m_tiles * g.num_n_tiles);
+      const int n_tile = g.m_fast ? wt / g.num_m_tiles : wt % g.num_n_tiles;
+      const int m_tile = g.m_fast ? wt % g.num_m_tiles : wt / g.num_n_tiles;
       const int acc = iter & 1;
       const int tile_row0 = m_tile * BM;
       const int colg0 = n_tile * BN + grp * 64;           // first column of this group
@@ -287,6 +289,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         if (!grp_active) continue;
 
+        if (gm && e.gm_cols) {
+          // transposed call: this thread owns ONE CHANNEL (row of C) and 32 consecutive points (columns) = whole
+          // patches: the max pool (utils.py:180,188) is pure register work, first index wins, no staging at all
+          if (grow < g.M) {
+            const float badd = e.row_bias ? __ldg(e.row_bias + grow) : 0.f;
+            const int S = e.gm_S, smask = S - 1;   // S: power of two <= 32
+            float mx = v[0];
+            int am = 0;
+#pragma unroll
+            for (int j = 1; j <= 32; ++j) {
+              if (j == 32 || (j & smask) == 0) {          // patch boundary: emit the finished patch
+                const int gs = j - S;
+                if (col0 + gs < g.N) {
+                  const size_t go = (size_t)((col0 + gs) / S) * e.gm_ld + grow;
+                  const float o = mx + badd;
+                  if (e.gm_out_f32) e.gm_out_f32[go] = o;
+                  if (e.gm_out_bf16) reinterpret_cast<__nv_bfloat16 *>(e.gm_out_bf16)[go] = __float2bfloat16(o);
+                  if (e.gm_argmax) e.gm_argmax[go] = (uint8_t)am;
+                }
+                if (j < 32) { mx = v[j]; am = 0; }
+              } else if (v[j] > mx) {
+                mx = v[j];
+                am = j & smask;
+              }
+            }
+          }
+          continue;
+        }
         // ------------- TMA epilogue: registers -> swizzled staging (this thread = one row).  Columns >= N inside
         // the box hold garbage/zeros; the TMA store clips them.
         if (gm) {   // raw accumulators for the column-wise max pool (biases are added after the max)
@@ -386,9 +416,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (e.out2) tma_store_2d(&tma_out2, bf_out2_box, colg0, tile_row0);
           bulk_commit();
         }
-        if (gm) {
+        if (gm && !e.gm_cols) {
           // per-patch max over gm_S rows on the fp32 accumulators, first index wins (torch.max, utils.py:180,188).
-          // thread t of the group: column t % 64, row half t / 64.
+          // thread t of the group: column t % 64, row quarter t / 64.
           const int t = (warp - 2 - grp * 8) * 32 + lane;
           const int cl = t & 63, col = colg0 + cl;
           if (col < g.N) {
@@ -469,8 +499,9 @@ using namespace vpf;
 extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, int b_mn, int ldb, int M, int N, int K,
                              int splits, const vpf_gemm_epilogue *epi, void *stream) {
   VPF_REQUIRE(A && B && epi && (epi->out || epi->gm_S > 0), "gemm: null pointer");
-  VPF_REQUIRE(epi->gm_S == 0 || ((epi->gm_S & (epi->gm_S - 1)) == 0 && epi->gm_S <= 32 && M % epi->gm_S == 0 && epi->mode == VPF_EPI_STORE && epi->alpha == 1.0f),
-              "gemm: max-pool epilogue needs S a power of two <= 32 dividing M, store mode, alpha 1");
+  VPF_REQUIRE(epi->gm_S == 0 || ((epi->gm_S & (epi->gm_S - 1)) == 0 && epi->gm_S <= 32 && (epi->gm_cols ? N : M) % epi->gm_S == 0 && epi->mode == VPF_EPI_STORE && epi->alpha == 1.0f),
+              "gemm: max-pool epilogue needs S a power of two <= 32 dividing the pooled dimension, store mode, alpha 1");
+  VPF_REQUIRE(!epi->gm_cols || (epi->gm_S > 0 && epi->out == nullptr), "gemm: gm_cols is a pool-only epilogue (out must be NULL)");
   VPF_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   VPF_REQUIRE(epi->mode == VPF_EPI_STORE || epi->mode == VPF_EPI_RESIDUAL || epi->mode == VPF_EPI_ATOMIC_ADD, "gemm: bad epilogue mode %d", epi->mode);
   VPF_REQUIRE(epi->mode != VPF_EPI_RESIDUAL || epi->resid, "gemm: residual epilogue needs resid");
@@ -503,6 +534,7 @@ extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, in
   g.num_m_tiles = ceil_div(M, BM);
   g.num_n_tiles = ceil_div(N, BN);
   g.kblocks = ceil_div(K, BK);
+  g.m_fast = (epi->gm_cols && N > M) ? 1 : 0;   // transposed pool: adjacent work items share the (large) activation tile
   if (splits < 1) {  // auto: fill the machine
     const int tiles = g.num_m_tiles * g.num_n_tiles;
     splits = epi->mode == VPF_EPI_ATOMIC_ADD ? max(1, min(g.kblocks, (2 * num_sms()) / max(1, tiles))) : 1;

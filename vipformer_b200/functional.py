@@ -162,7 +162,8 @@ def group2emb_fwd(nb, W, bn, cfg, training, save=True):
     y3 = _empty((R, 256), BF16, nb)
     ops.gemm(f2, W.w3[:, 128:], y3, rg_bias=u, rg_shift=int(math.log2(S)))
     h3, st3 = ops.bn_forward(y3, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, training, True)
-    # conv4 + max over the patch (utils.py:188): pooled in the epilogue, the [R, D] pre-pool tensor is never stored
+    # conv4 + max over the patch (utils.py:187-188): pooled from the fp32 accumulators in the GEMM epilogue, the [R, D]
+    # pre-pool tensor is never stored.  (The transposed, register-only variant `gm_cols=True` measured slower: 864 vs 600 us.)
     tok = _empty((Gt, D), F32, nb)
     am4 = _empty((Gt, D), torch.uint8, nb)
     ops.gemm(h3, W.w4, None, bias=W.b4, gm_S=S, gm_f32=tok, gm_argmax=am4)

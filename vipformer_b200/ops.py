@@ -19,7 +19,7 @@ class GemmEpilogue(ctypes.Structure):
                 ("rg_shift", _i), ("rg_ld", _i), ("op_id", ctypes.c_uint), ("alpha", _f), ("drop_p", _f),
                 ("out", _vp), ("out2", _vp), ("out_bf16", _vp), ("bias", _vp), ("rg_bias", _vp), ("aux", _vp),
                 ("resid", _vp), ("seed_ptr", _vp), ("gm_S", _i), ("gm_ld", _i), ("gm_out_f32", _vp), ("gm_out_bf16", _vp),
-                ("gm_argmax", _vp)]
+                ("gm_argmax", _vp), ("gm_cols", _i), ("row_bias", _vp)]
 
 
 def _dp(t):
@@ -29,7 +29,7 @@ def _dp(t):
 def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, lda=None, ldb=None, mode=EPI_STORE,
          bias=None, rg_bias=None, rg_shift=0, act=ACT_NONE, aux=None, aux_mode=AUX_NONE, out2=None, resid=None,
          out_bf16=None, alpha=1.0, drop_p=0.0, seed=None, op_id=0, splits=None, ldc=None, gm_S=0, gm_f32=None,
-         gm_bf16=None, gm_argmax=None):
+         gm_bf16=None, gm_argmax=None, gm_cols=False, row_bias=None):
     """out (op)= epilogue(alpha * A @ B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn); bf16."""
     _lib.require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -53,6 +53,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, M=None, N=None, K=None, lda=None,
         gm_any = gm_f32 if gm_f32 is not None else gm_bf16
         e.gm_S, e.gm_ld = gm_S, gm_any.stride(0)
         e.gm_out_f32, e.gm_out_bf16, e.gm_argmax = _dp(gm_f32), _dp(gm_bf16), _dp(gm_argmax)
+        e.gm_cols, e.row_bias = int(gm_cols), _dp(row_bias)
     e.aux_mode, e.ld_aux = aux_mode, (aux.stride(0) if aux is not None else 0)
     e.rg_shift, e.rg_ld = rg_shift, (rg_bias.stride(0) if rg_bias is not None else 0)
     e.op_id, e.alpha, e.drop_p = op_id, alpha, drop_p
