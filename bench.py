@@ -153,7 +153,8 @@ def run_ours(args):
     cfg = dict(CFG, b=b)
     pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)     # script values (scripts/pretrain/*.sh)
     eng = PretrainEngine(pc, im, batch_pairs=b, num_points=cfg["N"], img_size=cfg["img"], lr=1e-3, seed=1,
-                         use_cuda_graph=(not args.no_graph) and (world == 1 or args.graph))
+                         use_cuda_graph=(not args.no_graph) and (world == 1 or args.graph),
+                         overlap_branches=not args.no_overlap)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
 
     def synth_clouds(n):
@@ -239,7 +240,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": b, "global_pairs": b * world, "points": cfg["N"],
                        "parallelism": f"dp{world}", "negatives": "global (all-gather)" if eng.gather else "rank-local",
-                       "cuda_graph": eng.graph is not None, "dropout": "atten 0.1 / mlp 0.5",
+                       "two_stream_branches": eng.side is not None, "cuda_graph": eng.graph is not None, "dropout": "atten 0.1 / mlp 0.5",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 2 alternating input batches"},
             "e2e": {"value": e2e_value, "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps * 2),
@@ -283,8 +284,8 @@ def gemm_roofline(eng, load, pk, pk_kind):
         rec.append((e0, e1, 2.0 * M * N * K))
         return r
 
-    import vipformer_b200.functional as Fn
     ops.gemm = timed_gemm
+    side, eng.side = eng.side, None     # serial schedule: a launch timed while the other branch runs is not its own time
     try:
         for i in range(2):
             rec.clear()
@@ -293,6 +294,7 @@ def gemm_roofline(eng, load, pk, pk_kind):
             torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        eng.side = side
     t = sum(e0.elapsed_time(e1) for e0, e1, _ in rec) * 1e-3
     fl = sum(f for _, _, f in rec)
     ach = fl / t / 1e12
@@ -343,6 +345,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU (weak scaling)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the image branch on the main stream (no two-stream overlap)")
     ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also with world_size > 1 (default: eager there)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -247,3 +247,20 @@ def test_pool_head_block_backward():
     for k, p in head.named_parameters():
         tol = 3e-2 if k in ("5.weight", "3.weight") else 8e-2
         assert relfro(p.grad, sdr["h." + k].grad) < tol, (k, relfro(p.grad, sdr["h." + k].grad))
+
+
+def test_forward_bitwise_reproducible():
+    """Same weights, inputs, FPS start and dropout seed -> bit-identical forward outputs (no order-dependent fp32
+    reduction on the forward path; BatchNorm statistics combine in a fixed order inside a CTA and in fp64 across)."""
+    cfg = _synth.MODEL_CASES["small"]
+    torch.manual_seed(0)
+    pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)
+    pc, im = pc.cuda().train(), im.cuda().train()
+    pts, _, imgs = _synth.model_inputs(cfg)
+    pts, imgs = pts.cuda(), imgs.cuda()
+    pc.fps_start_idx = torch.arange(pts.shape[0], device="cuda") % cfg["N"]
+    with torch.no_grad():
+        ref = [t.clone() for t in (*pc(pts), *im(imgs))]
+        for _ in range(10):
+            cur = (*pc(pts), *im(imgs))
+            assert all(torch.equal(a, b) for a, b in zip(ref, cur))

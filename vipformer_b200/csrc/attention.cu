@@ -490,8 +490,8 @@ attn_bwd_dq_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__
 template <int NQW>
 __global__ void __launch_bounds__(32 * NQW)
 attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict__ K, const bf16 *__restrict__ V,
-                      int ldkv, const bf16 *__restrict__ dO, int lddo, const float *__restrict__ LSE,
-                      const float *__restrict__ delta, bf16 *__restrict__ dQ, int lddq, bf16 *__restrict__ dK,
+                      int ldkv, const bf16 *__restrict__ O, int ldo, const bf16 *__restrict__ dO, int lddo,
+                      const float *__restrict__ LSE, bf16 *__restrict__ dQ, int lddq, bf16 *__restrict__ dK,
                       bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, float scale, float drop_p,
                       const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
   extern __shared__ __align__(128) uint8_t attn_smem[];
@@ -517,11 +517,31 @@ attn_bwd_fused_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restric
   uint32_t qa[4][4], da[4][4];
   const int r0 = warp * 16 + (lane >> 2);   // this thread's first query row (second is +8)
   float lse[2], dl[2];
+  {
+    // delta_i = sum_d dO[i,d] O[i,d] for this warp's 16 rows: two lanes per row, 32 head-dim columns each
+    const int ri = warp * 16 + (lane >> 1), half = lane & 1;
+    float acc = 0.f;
+    if (ri < Lq) {
+      const uint4 *po = reinterpret_cast<const uint4 *>(O + ((size_t)b * Lq + ri) * ldo + h * HD + half * 32);
+      const uint4 *pd = reinterpret_cast<const uint4 *>(dO + ((size_t)b * Lq + ri) * lddo + h * HD + half * 32);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int i = r0 + q * 8;
-    lse[q] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
-    dl[q] = i < Lq ? delta[(size_t)bh * Lq + i] : 0.f;
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+        const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = __bfloat1622float2(ha[q]), fd = __bfloat1622float2(hd[q]);
+          acc += fa.x * fd.x + fa.y * fd.y;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);   // lanes 2r, 2r+1 now both hold delta of row warp*16 + r
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = r0 + q * 8;
+      lse[q] = i < Lq ? LSE[(size_t)bh * Lq + i] : INFINITY;
+      dl[q] = __shfl_sync(0xffffffffu, acc, 2 * ((lane >> 2) + q * 8));
+    }
   }
   float dq[8][4];
 #pragma unroll
@@ -682,10 +702,7 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE((ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddkv % 2) == 0, "attention_bwd: bad stride");
   if (B == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)B * Lq * H;
-  attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
-  VPF_TRY(check_launch("attn_delta_kernel"));
-#define FUSED_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
+#define FUSED_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)O, ldo, (const bf16 *)dO, lddo, LSE, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (Lq <= 128) {
     const int smem = (4 * 128 + 4 * 64) * HD * 2;
     VPF_TRY(set_smem(attn_bwd_fused_kernel<8>, smem));
@@ -699,6 +716,10 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
     return check_launch("attn_bwd_fused_kernel<10>");
   }
 #undef FUSED_ARGS
+  // two-kernel path (Lq > 160): delta = rowsum(dO * O) first, the fused kernel computes it itself
+  const long long total = (long long)B * Lq * H;
+  attn_delta_kernel<<<(unsigned)ceil_div(total, 256LL), 256, 0, st>>>((const bf16 *)O, ldo, (const bf16 *)dO, lddo, delta_ws, H, Lq, total);
+  VPF_TRY(check_launch("attn_delta_kernel"));
 #define DKV_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
 #define DQ_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)dO, lddo, LSE, delta_ws, (bf16 *)dQ, lddq, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (use8(Lk)) {

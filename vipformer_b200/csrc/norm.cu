@@ -482,11 +482,15 @@ colreduce_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *
                       const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                       const float *__restrict__ rstd, int relu, double *__restrict__ out0, double *__restrict__ out1,
                       float *__restrict__ out0_f32, long long R, int C, int rows_per_cta) {
-  extern __shared__ float s_red[];   // [2][cgx*8]
+  // [2][ny][cgx*8]: one slot per thread, summed in a fixed order below, so that the forward BatchNorm statistics
+  // (and with them the whole forward pass) are bitwise reproducible up to the fp64 atomics across CTAs
+  extern __shared__ float s_red[];
   const ColMap m = col_map(C);
   const int ncol_cta = m.cgx * 8;
-  for (int i = threadIdx.x; i < 2 * ncol_cta; i += 256) s_red[i] = 0.f;
-  __syncthreads();
+  if (!m.active && m.ty < m.ny) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_red[m.ty * ncol_cta + m.tx * 8 + q] = s_red[(m.ny + m.ty) * ncol_cta + m.tx * 8 + q] = 0.f;
+  }
   if (m.active) {
     float sc[8], sh[8], mu[8], rs[8];
     if (MODE == 1) {
@@ -530,19 +534,20 @@ colreduce_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *
         }
       }
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      atomicAdd(&s_red[m.tx * 8 + q], a0[q]);
-      atomicAdd(&s_red[ncol_cta + m.tx * 8 + q], a1[q]);
-    }
+    float4 *p0 = reinterpret_cast<float4 *>(s_red + m.ty * ncol_cta + m.tx * 8);
+    float4 *p1 = reinterpret_cast<float4 *>(s_red + (m.ny + m.ty) * ncol_cta + m.tx * 8);
+    p0[0] = make_float4(a0[0], a0[1], a0[2], a0[3]); p0[1] = make_float4(a0[4], a0[5], a0[6], a0[7]);
+    p1[0] = make_float4(a1[0], a1[1], a1[2], a1[3]); p1[1] = make_float4(a1[4], a1[5], a1[6], a1[7]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncol_cta; i += 256) {
     const int c = blockIdx.y * ncol_cta + i;
     if (c >= C) continue;
-    if (out0) atomicAdd(out0 + c, (double)s_red[i]);
-    if (out1) atomicAdd(out1 + c, (double)s_red[ncol_cta + i]);
-    if (out0_f32) atomicAdd(out0_f32 + c, s_red[i]);
+    float t0 = 0.f, t1 = 0.f;
+    for (int y = 0; y < m.ny; ++y) { t0 += s_red[y * ncol_cta + i]; t1 += s_red[(m.ny + y) * ncol_cta + i]; }
+    if (out0) atomicAdd(out0 + c, (double)t0);
+    if (out1) atomicAdd(out1 + c, (double)t1);
+    if (out0_f32) atomicAdd(out0_f32 + c, t0);
   }
 }
 
@@ -621,7 +626,7 @@ static inline void bf16_col_cfg(long long R, int C, dim3 &grid, int &rows_per_ct
   const long long want_ctas = max(1, num_sms() * 6 / gy);
   rows_per_cta = (int)max((long long)ny * 8, ceil_div(R, want_ctas));
   grid = dim3((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
-  smem = 2 * cgx * 8 * (int)sizeof(float);
+  smem = 2 * ny * cgx * 8 * (int)sizeof(float);   // colreduce: one slot per thread and statistic
 }
 
 __global__ void cast_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, size_t n) {
@@ -805,6 +810,7 @@ int vpf_gelu_bwd(const void *dh_bf16, const void *z_bf16, void *dz_bf16, float *
   if (R == 0 || C == 0) return VPF_OK;
   dim3 g8; int rpc, smem;
   bf16_col_cfg(R, C, g8, rpc, smem);
+  smem = min(C / 8, 256) * 8 * (int)sizeof(float);
   gelu_bwd_kernel<<<g8, 256, smem, (cudaStream_t)stream>>>((const bf16 *)dh_bf16, (const bf16 *)z_bf16, (bf16 *)dz_bf16, colsum, R, C, rpc);
   return check_launch("gelu_bwd_kernel");
 }

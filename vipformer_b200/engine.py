@@ -24,7 +24,7 @@ F32 = torch.float32
 class PretrainEngine:
     def __init__(self, pc_model, img_model, *, batch_pairs, num_points, img_size=144, lr=1e-3, betas=(0.9, 0.999),
                  eps=1e-8, weight_decay=1e-2, temperature=0.1, cmid_weight=1.0, gather_distributed=None,
-                 use_cuda_graph=True, seed=0, device=None, images_nchw=True):
+                 use_cuda_graph=True, seed=0, device=None, images_nchw=True, overlap_branches=True):
         import torch.distributed as dist
 
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -41,6 +41,10 @@ class PretrainEngine:
                 self.dist.broadcast(p.data, src=0)
             for b in self.root.buffers():
                 self.dist.broadcast(b.data, src=0)
+        # dropout site ids in module order, so a run depends on (weights, seed) only and not on how many layers the
+        # process constructed before
+        for i, m in enumerate(m for m in self.root.modules() if hasattr(m, "_op_base")):
+            m._op_base = 8 * (i + 1)
         self.arena = params.prepare(self.root, self.device)
         self.arena.ensure_grads()
         self.arena.refresh_shadows(force=True)
@@ -68,6 +72,7 @@ class PretrainEngine:
         self.gen.manual_seed(1234 + self.rank)
         self.use_graph = use_cuda_graph
         self.graph = None
+        self.side = torch.cuda.Stream(device=self.device) if overlap_branches else None
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
@@ -79,11 +84,24 @@ class PretrainEngine:
         self.arena.zero_grads()                           # optimizer.zero_grad (pretrain.py:174)
         torch.randint(0, self.N, (2 * self.b,), dtype=torch.long, device=self.device, generator=self.gen, out=self.start)
         self.pc_model.fps_start_idx = self.start          # utils.py:71, drawn on the device
-        pc_feats, _ = self.pc_model(self.pc_in)           # pretrain.py:186
         imgs = self.img_in.permute(0, 2, 3, 1) if self.images_nchw else self.img_in   # pretrain.py:179
-        img_feats, _ = self.img_model(imgs)               # pretrain.py:199
+        if self.side is not None:
+            # the two encoders are independent until the loss: the image branch runs on a second stream so that its
+            # kernels fill the partial last waves / launch gaps of the point-cloud branch (autograd replays each
+            # node's backward on the stream its forward ran on, so the backward overlaps the same way)
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                img_feats, _ = self.img_model(imgs)       # pretrain.py:199
+            pc_feats, _ = self.pc_model(self.pc_in)       # pretrain.py:186
+            cur.wait_stream(self.side)
+        else:
+            pc_feats, _ = self.pc_model(self.pc_in)
+            img_feats, _ = self.img_model(imgs)
         losses = pretrain_loss(pc_feats, img_feats, self.temperature, self.cmid_weight, self.gather)
         losses[0].backward()                              # pretrain.py:209
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
         if self.dist:                                     # DDP gradient all-reduce (mean), one flat buffer
             self.dist.all_reduce(self.arena.flat_g, op=self.dist.ReduceOp.AVG)
         ops.adamw(self.arena.flat_p, self.arena.flat_g, self.m, self.v, self.arena.flat_bf, self.lr, self.state[:1],
