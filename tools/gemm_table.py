@@ -10,7 +10,7 @@ from vipformer_b200.engine import PretrainEngine
 b = 256
 cfg = dict(bench.CFG, b=b)
 pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)
-eng = PretrainEngine(pc, im, batch_pairs=b, num_points=cfg["N"], img_size=cfg["img"], use_cuda_graph=False)
+eng = PretrainEngine(pc, im, batch_pairs=b, num_points=cfg["N"], img_size=cfg["img"], use_cuda_graph=False, overlap_branches=False)
 g = torch.Generator(device="cuda").manual_seed(1)
 eng.pc_in.copy_(torch.randn(eng.pc_in.shape, device="cuda", generator=g) * 0.3)
 eng.img_in.copy_(torch.randn(eng.img_in.shape, device="cuda", generator=g))

@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("VPF_NVCC_EXTRA", "").split()   # e.g. -DVPF_GEMM_TIMING for tools/gemm_phase_timing.py
 
 
 def sources():
