@@ -155,7 +155,9 @@ __device__ __forceinline__ void tma_reduce_add_2d_s(const CUtensorMap *m, uint32
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_s), "r"(c0), "r"(c1) : "memory");
 }
 
-enum { EK_GENERIC = 0, EK_BF16 = 1, EK_F32 = 2, EK_RESID = 3 };   // warp-autonomous epilogue kinds
+// warp-autonomous epilogue kinds: generic, bf16 store, fp32 store / split-K reduce, residual (+dropout), and the three
+// Group2Emb convolutions (bf16 store + per-patch max, per-patch max only, bf16 store + per-group bias)
+enum { EK_GENERIC = 0, EK_BF16 = 1, EK_F32 = 2, EK_RESID = 3, EK_POOL_OUT = 4, EK_POOL = 5, EK_RG = 6 };
 
 template <int BN_T, int EK>
 __device__ __forceinline__ void epilogue_wa(const GemmArgs &g, const CUtensorMap *tma_out, const CUtensorMap *tma_resid,
@@ -170,14 +172,14 @@ __device__ __forceinline__ void epilogue_wa(const GemmArgs &g, const CUtensorMap
   // EK_GENERIC reads every epilogue option at run time; the other kinds fix them at compile time, which removes the
   // option tests (and the dead code behind them) from the per-chunk instruction stream
   constexpr bool G = EK == EK_GENERIC;
-  const bool pool = G ? e.gm_S > 0 : false;
+  const bool pool = G ? e.gm_S > 0 : (EK == EK_POOL || EK == EK_POOL_OUT);
   const bool resid = G ? e.mode == VPF_EPI_RESIDUAL : EK == EK_RESID;
   const bool has_aux = G ? e.aux_mode != VPF_AUX_NONE : false;
   const bool need_ld = resid || has_aux;
-  const bool out_is_f32 = G ? (e.mode != VPF_EPI_STORE || e.out_f32) : EK != EK_BF16;
-  const bool has_out = G ? e.out != nullptr : true;
+  const bool out_is_f32 = G ? (e.mode != VPF_EPI_STORE || e.out_f32) : (EK == EK_F32 || EK == EK_RESID);
+  const bool has_out = G ? e.out != nullptr : EK != EK_POOL;
   const bool has_alpha = G ? e.alpha != 1.0f : false;
-  const bool has_rg = G ? e.rg_bias != nullptr : false;
+  const bool has_rg = G ? e.rg_bias != nullptr : EK == EK_RG;
   const int act = G ? e.act : (int)VPF_ACT_NONE;
   const bool atomic = (G || EK == EK_F32) ? e.mode == VPF_EPI_ATOMIC_ADD : false;
   const uint32_t my_s = stg_s + (uint32_t)(ew * g.stg_nbuf * g.stg_buf_bytes);
@@ -1019,8 +1021,12 @@ extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, in
   g.splits = ceil_div(g.kblocks, g.kblocks_per_split);
   // epilogue kind: the three shapes that make up the training step are compiled without run-time option tests
   int ek = EK_GENERIC;
-  if (wa && epi->alpha == 1.0f && epi->act == VPF_ACT_NONE && !epi->rg_bias && !has_aux && !pool && epi->out) {
-    if (epi->mode == VPF_EPI_RESIDUAL) ek = EK_RESID;
+  if (wa && epi->alpha == 1.0f && epi->act == VPF_ACT_NONE && !has_aux) {
+    if (pool) {
+      if (!epi->rg_bias && (!epi->out || !out_f32)) ek = epi->out ? EK_POOL_OUT : EK_POOL;
+    } else if (epi->rg_bias) {
+      if (epi->mode == VPF_EPI_STORE && !out_f32) ek = EK_RG;
+    } else if (epi->mode == VPF_EPI_RESIDUAL) ek = EK_RESID;
     else if (out_f32) ek = EK_F32;
     else ek = EK_BF16;
   }
@@ -1042,6 +1048,9 @@ extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, in
     if (ek == EK_BF16) VPF_LAUNCH(BNV, STV, EK_BF16);               \
     else if (ek == EK_F32) VPF_LAUNCH(BNV, STV, EK_F32);            \
     else if (ek == EK_RESID) VPF_LAUNCH(BNV, STV, EK_RESID);        \
+    else if (ek == EK_POOL_OUT) VPF_LAUNCH(BNV, STV, EK_POOL_OUT);  \
+    else if (ek == EK_POOL) VPF_LAUNCH(BNV, STV, EK_POOL);          \
+    else if (ek == EK_RG) VPF_LAUNCH(BNV, STV, EK_RG);              \
     else VPF_LAUNCH(BNV, STV, EK_GENERIC);                          \
   } while (0)
   if (!wa) VPF_LAUNCH(128, 4, -1);
