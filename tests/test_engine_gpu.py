@@ -68,3 +68,31 @@ def test_engine_two_stream_overlap_matches_serial(graph):
     assert torch.allclose(h0, h1, rtol=1e-5, atol=1e-5), (h0, h1)
     assert not torch.allclose(h0[0], h0[1], rtol=1e-4, atol=1e-4)   # fresh dropout masks every step
     assert ((g0 - g1).norm() / g0.norm()).item() < 1e-4
+
+
+def test_engine_prefetched_host_steps_match_synchronous():
+    """step_host_prefetched (H2D of the next batch on a copy stream) must consume exactly the batches it was given, in
+    order: same losses as the synchronous step_host on the same sequence of batches (lr = 0, fixed weights)."""
+    cfg = _synth.MODEL_CASES["small"]
+    b = cfg["b"]
+    batches = []
+    for k in range(3):
+        g = torch.Generator().manual_seed(50 + k)
+        pts = torch.randn((2 * b, cfg["N"], 3), generator=g) * 0.4
+        imgs = torch.randn((b, 3, 144, 144), generator=g)
+        batches.append((pts[:b].contiguous().pin_memory(), pts[b:].contiguous().pin_memory(), imgs.pin_memory()))
+    runs = []
+    for mode in ("sync", "prefetch"):
+        torch.manual_seed(0)
+        eng, *_ = _engine(False, seed=5, lr=0.0)
+        out = []
+        if mode == "sync":
+            for bt in batches:
+                out.append(eng.step_host(*bt).clone())
+        else:
+            eng.prefetch_host(*batches[0])
+            for k in range(3):
+                out.append(eng.step_host_prefetched(batches[k + 1] if k + 1 < 3 else None).clone())
+        runs.append(torch.stack(out))
+    assert torch.allclose(runs[0], runs[1], rtol=1e-5, atol=1e-5), runs
+    assert not torch.allclose(runs[0][0], runs[0][1], rtol=1e-3, atol=1e-3)   # the batches do differ

@@ -73,6 +73,7 @@ class PretrainEngine:
         self.use_graph = use_cuda_graph
         self.graph = None
         self.side = torch.cuda.Stream(device=self.device) if overlap_branches else None
+        self._copy_stream, self._staged = None, False
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
@@ -137,6 +138,46 @@ class PretrainEngine:
             self._step_body()
         self.steps_done += 1
         return self.losses
+
+    # ------------------------------------------------------------------------------- pipelined host input (e2e)
+    def prefetch_host(self, pc_t1, pc_t2, imgs):
+        """Start the H2D copy of the NEXT step's inputs (pinned host tensors, same shapes as step_host) on a copy
+        stream into a staging buffer; it overlaps whatever the compute stream is running.  What a DataLoader with
+        pin_memory + non_blocking copies + prefetch gives the reference (pretrain.py:173-179)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pc_stage = torch.empty_like(self.pc_in)
+            self._img_stage = torch.empty_like(self.img_in)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        b = self.b
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)                   # the previous staged batch has been consumed
+        with torch.cuda.stream(cs):
+            self._pc_stage[:b].copy_(pc_t1, non_blocking=True)
+            self._pc_stage[b:].copy_(pc_t2, non_blocking=True)
+            self._img_stage.copy_(imgs, non_blocking=True)
+            self._stage_ready.record(cs)
+        self._staged = True
+
+    def step_host_prefetched(self, next_batch=None):
+        """One step on the batch staged by prefetch_host(); starts the copy of `next_batch` (a (pc_t1, pc_t2, imgs)
+        tuple of pinned host tensors) before the step is launched, then reads the losses back (synchronises)."""
+        if not self._staged:
+            raise RuntimeError("step_host_prefetched: no staged batch; call prefetch_host() first")
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready)
+        self.pc_in.copy_(self._pc_stage, non_blocking=True)      # device-to-device, ~25 us
+        self.img_in.copy_(self._img_stage, non_blocking=True)
+        self._stage_free.record(cur)
+        self._staged = False
+        if next_batch is not None:
+            self.prefetch_host(*next_batch)
+        self.step()
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        cur.synchronize()
+        return self.losses_host
 
     def step_host(self, pc_t1, pc_t2, imgs):
         """End-to-end step from (pinned) HOST tensors: H2D copies, the step, D2H read of the losses (synchronises).
