@@ -4,11 +4,15 @@
 //                        resident in registers (running distance) and shared
 //                        memory (centroid lookup); argmax by two redux.sync
 //                        per level, one __syncthreads per iteration.
-//   K2 knn_group_kernel  kNN selection (warp-per-query streaming top-32 over a
-//                        shared-memory copy of the cloud) fused with the patch
-//                        gather and the reference's slot-0..2 centre
-//                        subtraction; the [B,G,N] distance matrix the reference
-//                        materialises never exists.
+//   K2 knn_group_kernel  kNN selection, one warp per query over a shared-memory
+//                        copy of the cloud: pass 1 finds a threshold that at
+//                        least 32 points pass (the 32nd smallest of the 64
+//                        lane-local two smallest distances), pass 2 compacts
+//                        the ~40 candidates under it, a rank count orders them
+//                        (streaming sorted insertion is kept as the fallback);
+//                        fused with the patch gather and the reference's
+//                        slot-0..2 centre subtraction; the [B,G,N] distance
+//                        matrix the reference materialises never exists.
 //
 // Reference: vipformer/model/pointcloud/utils.py:6-141.  Arithmetic is pinned
 // exactly as oracle/tokenizer_oracle.c states it (explicit __fmul_rn/__fadd_rn
@@ -101,6 +105,119 @@ fps_kernel(const float *__restrict__ pts, int N, int C, int npoint,
 // ------------------------------------------------- K2: kNN + gather (fused) ---
 // utils.py:107-141 (selection) and utils.py:22-36 (gather + slot quirk).
 // grid = (B, splits); warp w of split y handles queries q = y*per + w, +8, ...
+constexpr int kKnnCap = 128;   // candidate slots per warp (two-pass selection); more candidates => streaming fallback
+
+// expanded-form distance, arithmetic order pinned to oracle/tokenizer_oracle.c (utils.py:138-140)
+__device__ __forceinline__ float knn_dist(const float4 P, float cx, float cy, float cz, float c2) {
+  const float dot = fmaf(cz, P.z, fmaf(cy, P.y, __fmul_rn(cx, P.x)));
+  return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), c2), P.w);
+}
+
+// ascending bitonic sort of one float per lane
+__device__ __forceinline__ float warp_sort_asc(float v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float o = __shfl_xor_sync(kFull, v, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0 || k == 32);
+      v = keep_min ? fminf(v, o) : fmaxf(v, o);
+    }
+  }
+  return v;
+}
+
+// Streaming selection: lane l keeps the l-th smallest key (ordered distance bits, index) seen so far; candidates that
+// beat the current worst are inserted by ballot + shuffle.  Returns this lane's index (lane < nsample).
+__device__ __forceinline__ uint32_t knn_select_stream(const float4 *s_pt, int N, int nsample, float cx, float cy, float cz,
+                                                      float c2, int lane) {
+  uint32_t Lhi = 0xff800000u /* f2ord(+inf) */, Llo = 0xffffffffu;
+  float worst = __int_as_float(0x7f800000);
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < N;
+    const float d = knn_dist(s_pt[valid ? i : 0], cx, cy, cz, c2);
+    unsigned mask = __ballot_sync(kFull, valid && d <= worst);
+    if (mask) {
+      const uint32_t khi = f2ord(d), klo = (uint32_t)i;
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t h = __shfl_sync(kFull, khi, src), l = __shfl_sync(kFull, klo, src);
+        const bool less = (Lhi < h) || (Lhi == h && Llo < l);
+        const int pos = __popc(__ballot_sync(kFull, less));
+        if (pos < nsample) {
+          const uint32_t uhi = __shfl_up_sync(kFull, Lhi, 1), ulo = __shfl_up_sync(kFull, Llo, 1);
+          if (lane == pos) { Lhi = h; Llo = l; }
+          else if (lane > pos) { Lhi = uhi; Llo = ulo; }
+        }
+      }
+      worst = ord2f(__shfl_sync(kFull, Lhi, nsample - 1));
+    }
+  }
+  return Llo;
+}
+
+// Two-pass selection.  Pass 1: every lane tracks the two smallest distances among its N/32 points; the 32nd smallest
+// of those 64 values (bitonic half-cleaner of the two lane-sorted sequences) is a threshold tau that at least 32
+// points pass, and on average only ~40 do.  Pass 2 recomputes the distances (bit-identical instruction sequence),
+// compacts the points with d <= tau into shared memory as (ordered distance bits, index) keys, and a rank count over
+// the candidates yields the nsample smallest in (distance, index) order -- the same total order as the streaming
+// selection and as the oracle.  Returns false when the candidate list overflows (heavy ties): caller falls back.
+__device__ __forceinline__ bool knn_select_twopass(const float4 *s_pt, int N, int nsample, float cx, float cy, float cz,
+                                                   float c2, int lane, unsigned long long *cand, uint32_t *sel,
+                                                   uint32_t &Llo) {
+  const float inf = __int_as_float(0x7f800000);
+  float m1 = inf, m2 = inf;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    if (i < N) {
+      const float d = knn_dist(s_pt[i], cx, cy, cz, c2);
+      const float t = fmaxf(m1, d);
+      m1 = fminf(m1, d);
+      m2 = fminf(m2, t);
+    }
+  }
+  const float a = warp_sort_asc(m1, lane), bs = warp_sort_asc(m2, lane);
+  const float lo32 = fminf(a, __shfl_sync(kFull, bs, 31 - lane));       // the 32 smallest of the 64 values (as a set)
+  const float tau = ord2f(__reduce_max_sync(kFull, f2ord(lo32)));        // ... and the largest of them
+  int cnt = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < N;
+    const float d = knn_dist(s_pt[valid ? i : 0], cx, cy, cz, c2);
+    const bool pred = valid && d <= tau;
+    const unsigned mask = __ballot_sync(kFull, pred);
+    if (mask) {
+      if (pred) {
+        const int pos = cnt + __popc(mask & lt);
+        if (pos < kKnnCap) cand[pos] = ((unsigned long long)f2ord(d) << 32) | (uint32_t)i;
+      }
+      cnt += __popc(mask);
+    }
+  }
+  if (cnt > kKnnCap) return false;     // warp-uniform
+  __syncwarp();
+  // rank of each candidate among all candidates; lane owns candidates lane, lane + 32, ...
+  for (int j0 = 0; j0 < cnt; j0 += 64) {
+    const int ja = j0 + lane, jb = j0 + 32 + lane;
+    const unsigned long long ca = ja < cnt ? cand[ja] : ~0ull, cb = jb < cnt ? cand[jb] : ~0ull;
+    int ra = 0, rb = 0;
+    for (int m = 0; m < cnt; ++m) {
+      const unsigned long long x = cand[m];     // broadcast read
+      ra += x < ca;
+      rb += x < cb;
+    }
+    if (ja < cnt && ra < nsample) sel[ra] = (uint32_t)ca;
+    if (jb < cnt && rb < nsample) sel[rb] = (uint32_t)cb;
+  }
+  __syncwarp();
+  Llo = lane < nsample ? sel[lane] : 0xffffffffu;
+  __syncwarp();                        // sel aliases the gather staging buffer
+  return true;
+}
+
 __global__ void __launch_bounds__(kKnnThreads)
 knn_group_kernel(const float *__restrict__ pts, int N, int C,
                  const float *__restrict__ queries, int Q, int Cq, int nsample,
@@ -108,6 +225,7 @@ knn_group_kernel(const float *__restrict__ pts, int N, int C,
                  float *__restrict__ neighbors) {
   extern __shared__ float4 s_pt[];  // [N] (x, y, z, |p|^2)
   __shared__ float s_out[kKnnThreads / 32][32 * 3];
+  __shared__ unsigned long long s_cand[kKnnThreads / 32][kKnnCap];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -121,39 +239,15 @@ knn_group_kernel(const float *__restrict__ pts, int N, int C,
 
   const int q_begin = blockIdx.y * q_per_cta;
   const int q_end = min(Q, q_begin + q_per_cta);
-  const uint32_t kEmptyHi = 0xff800000u;  // f2ord(+inf)
 
   for (int q = q_begin + warp; q < q_end; q += kKnnThreads / 32) {
     const float *c = queries + ((size_t)b * Q + q) * Cq;
     const float cx = c[0], cy = c[1], cz = c[2];
     const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));  // utils.py:139
-    uint32_t Lhi = kEmptyHi, Llo = 0xffffffffu;  // lane l holds the l-th smallest key so far
-    float worst = __int_as_float(0x7f800000);
-
-    for (int base = 0; base < N; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < N;
-      const float4 P = s_pt[valid ? i : 0];
-      const float dot = fmaf(cz, P.z, fmaf(cy, P.y, __fmul_rn(cx, P.x)));           // utils.py:138
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), c2), P.w);         // utils.py:138-140
-      unsigned mask = __ballot_sync(kFull, valid && d <= worst);
-      if (mask) {
-        const uint32_t khi = f2ord(d), klo = (uint32_t)i;
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const uint32_t h = __shfl_sync(kFull, khi, src), l = __shfl_sync(kFull, klo, src);
-          const bool less = (Lhi < h) || (Lhi == h && Llo < l);
-          const int pos = __popc(__ballot_sync(kFull, less));
-          if (pos < nsample) {
-            const uint32_t uhi = __shfl_up_sync(kFull, Lhi, 1), ulo = __shfl_up_sync(kFull, Llo, 1);
-            if (lane == pos) { Lhi = h; Llo = l; }
-            else if (lane > pos) { Lhi = uhi; Llo = ulo; }
-          }
-        }
-        worst = ord2f(__shfl_sync(kFull, Lhi, nsample - 1));
-      }
-    }
+    uint32_t Llo;   // lane l: index of the l-th nearest point by (distance, index)
+    if (N < 64 || !knn_select_twopass(s_pt, N, nsample, cx, cy, cz, c2, lane, s_cand[warp],
+                                      reinterpret_cast<uint32_t *>(s_out[warp]), Llo))
+      Llo = knn_select_stream(s_pt, N, nsample, cx, cy, cz, c2, lane);
 
     const size_t row = (size_t)b * Q + q;
     if (knn_idx && lane < nsample) knn_idx[row * nsample + lane] = (int64_t)Llo;
@@ -238,7 +332,7 @@ static int launch_knn(const float *pts, int B, int N, int C, const float *querie
                       int nsample, int64_t *knn_idx, float *neighbors, cudaStream_t st) {
   if (B == 0 || Q == 0) return VPF_OK;
   const size_t smem = (size_t)N * sizeof(float4);
-  if (smem > 48 * 1024)
+  if (smem + 12 * 1024 > 48 * 1024)   // the kernel also holds ~11 KB of static shared memory (candidates, gather staging)
     VPF_CUDA_TRY(cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // enough CTAs for >= 2 waves on small batches; a split re-stages the cloud (cheap)
   const int warps = kKnnThreads / 32;
