@@ -955,8 +955,9 @@ extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, in
   const bool pool = epi->gm_S > 0 && !epi->gm_cols;
   const bool has_aux = epi->aux_mode != VPF_AUX_NONE;
   const bool wa = g.tma_epi && !epi->out2 && !epi->gm_cols;   // warp-autonomous epilogue (everything the step uses)
-  // measured per shape class (tools/gemm_table.py, tools/gemm_sweep.py): the wide tile wins for K >= 512 and for the
-  // pool-only epilogue; K <= 256 GEMMs are epilogue-bound and want two staging buffers; split-K wants pipeline depth.
+  // measured per shape class (tools/gemm_table.py, tools/gemm_sweep.py) with the warp-autonomous epilogue: the wide
+  // tile (25 % less shared-memory traffic per FLOP) wins for K >= 256 and for bf16 outputs at any K; fp32 outputs with
+  // K < 256 stay narrow with two staging buffers; split-K wants pipeline depth.
   // VPF_GEMM_BN=128|256 overrides the tile width (experiments).
   static const int force_bn = [] { const char *v = getenv("VPF_GEMM_BN"); return v ? atoi(v) : 0; }();
   int variant = 0;   // 0: <128,4>  1: <128,3>  2: <256,3>
@@ -968,7 +969,8 @@ extern "C" int vpf_gemm_bf16(const void *A, int a_mn, int lda, const void *B, in
     if (has_aux) { g.stg_off_aux = cb; cb += 2048; }                   // bf16 aux chunk
     g.stg_buf_bytes = cb;
     const bool wide_ok = N % 256 == 0 && 16 * cb <= Cfg<256, 3>::kStgBytes;
-    bool wide = wide_ok && ((epi->mode != VPF_EPI_ATOMIC_ADD && K >= 512) || (pool && !epi->out));
+    // (split-K: the wide tile halves the tile count, which only pays when enough tiles are left to spread over the SMs)
+    bool wide = wide_ok && (epi->mode == VPF_EPI_ATOMIC_ADD ? (long long)M * N >= 512LL * 256 : (K >= 256 || !out_f32));
     if (force_bn == 128) wide = false;
     if (force_bn == 256) wide = wide_ok;
     if (wide) variant = 2;
