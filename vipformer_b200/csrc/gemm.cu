@@ -2,20 +2,21 @@
 //
 //   C[M,N] (op)= epilogue( alpha * sum_k A(m,k) * B(n,k) )
 //
-// Persistent, warp-specialised kernel, one CTA per SM (320 threads):
-//   warp 0      TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage ring of (A,B) k-blocks
-//   warp 1      MMA issuer     tcgen05.mma cta_group::1, M=128 N=128 K=16, accumulators in TMEM; two 128-column
+// Persistent, warp-specialised kernel, one CTA per SM (576 threads), template <BN, STAGES, EK>:
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, ring of (A,B) 64-wide k-blocks
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1, M=128 N=BN (128 or 256) K=16, accumulators in TMEM; two
 //                              accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..17 epilogue       two groups of 8 warps, each group owning 64 of the tile's 128 columns (one warp per
-//                              TMEM lane quadrant and 32-column chunk).  Everything the epilogue touches in HBM moves by TMA:
-//                                - residual (fp32) and aux (bf16: saved pre-activation / ReLU source) tiles are
-//                                  PREFETCHED into shared memory while the MMA of the same tile is still running,
-//                                - results are written to a 128B-swizzled staging tile and leave by
-//                                  cp.async.bulk.tensor store (bf16 / fp32) or cp.reduce.async.bulk.tensor .add
-//                                  (split-K weight gradients), so M/N tails are clipped by the TMA unit,
-//                                - the per-patch max pool (utils.py:180,188) reads the staged fp32 tile column-wise.
-//                              A thread owns one accumulator ROW (tcgen05.ld 32x32b); the XOR swizzle makes its
-//                              16-byte row pieces bank-conflict free.
+//   warps 2..17 epilogue       EK >= 0: warp-autonomous (epilogue_wa): every warp owns a 32-row x 32-column chunk end
+//                              to end -- TMEM quadrant, private staging slots, its own bulk stores / reduce-adds and
+//                              residual / aux bulk loads -- no group barrier in the steady state; the epilogue
+//                              options of the common kinds are compile-time constants.
+//                              EK < 0: lock-step fallback (unaligned outputs, out2, transposed pool): two groups of
+//                              8 warps, each owning 64 of the tile's 128 columns, staged 128x64 boxes, one elected
+//                              TMA issue per group.
+//                              Either way a thread owns one accumulator ROW (tcgen05.ld 32x32b), results leave by
+//                              cp.async.bulk.tensor store or cp.reduce.async.bulk.tensor .add (split-K weight
+//                              gradients) so M/N tails are clipped by the TMA unit, and the per-patch max pool
+//                              (utils.py:180,188) reads the staged fp32 chunk column-wise.
 //
 // Both operands may be K-major (row-major [rows][K]) or MN-major ([K][rows]); that covers the forward (X.W^T), the
 // data gradient (dY.W) and the weight gradient (dY^T.X) of every Linear / 1x1-Conv on the ViPFormer hot path
