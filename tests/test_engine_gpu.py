@@ -67,7 +67,7 @@ def test_engine_two_stream_overlap_matches_serial(graph):
     (h0, g0), (h1, g1) = runs
     assert torch.allclose(h0, h1, rtol=1e-5, atol=1e-5), (h0, h1)
     assert not torch.allclose(h0[0], h0[1], rtol=1e-4, atol=1e-4)   # fresh dropout masks every step
-    assert ((g0 - g1).norm() / g0.norm()).item() < 1e-4
+    assert ((g0 - g1).norm() / g0.norm()).item() < 5e-4   # fp32 atomics of the split-K reductions
 
 
 def test_engine_prefetched_host_steps_match_synchronous():
