@@ -224,6 +224,274 @@ linear3_bn_bwd_kernel(const bf16 *__restrict__ dh, const float *__restrict__ p, 
     }
   }
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Channel-stationary versions of the K=3 kernels.  A thread owns CH consecutive output channels for the whole kernel
+// (weights, bias and BatchNorm constants in registers, 16- / 8-byte accesses to the [R, Co] bf16 tensor) and strides
+// the rows; Co/CH lanes cover one row, 256/(Co/CH) rows are in flight per pass, U passes are unrolled.  The scalar
+// kernels above (one channel per thread, every constant re-read from global memory per element, 2-byte accesses) ran
+// at 9-15 % of the HBM roofline; they stay as the fallback for channel counts the vector layout does not divide.
+struct L3Map { int lanes, ny, tx, ty, c0; };
+template <int CH>
+__device__ __forceinline__ L3Map l3_map(int Co) {
+  L3Map m;
+  m.lanes = Co / CH;
+  m.ny = 256 / m.lanes;
+  m.tx = threadIdx.x % m.lanes;
+  m.ty = threadIdx.x / m.lanes;
+  m.c0 = m.tx * CH;
+  return m;
+}
+static inline bool l3_vec_ok(int Co, int CH) { return Co % CH == 0 && Co / CH <= 256 && 256 % (Co / CH) == 0; }
+
+__device__ __forceinline__ void unpack8_bf16(const uint4 u, float *f) {
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float *f) {
+  uint4 u;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return u;
+}
+
+__global__ void __launch_bounds__(256)
+linear3_fwd_vec_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
+                       const float *__restrict__ scale, const float *__restrict__ shift, bf16 *__restrict__ pre,
+                       bf16 *__restrict__ actout, int act, long long R, int Co, int rows_per_cta) {
+  constexpr int CH = 8, U = 4;
+  const L3Map m = l3_map<CH>(Co);
+  float w0[CH], w1[CH], w2[CH], bb[CH], sc[CH], sh[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = m.c0 + k;
+    w0[k] = w[c * 3]; w1[k] = w[c * 3 + 1]; w2[k] = w[c * 3 + 2]; bb[k] = b[c];
+    sc[k] = scale ? scale[c] : 1.f; sh[k] = scale ? shift[c] : 0.f;
+  }
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long r = row0 + m.ty; r < row1; r += (long long)U * m.ny) {
+    float x0[U], x1[U], x2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * m.ny;
+      if (rr < row1) { const float *q = p + (size_t)rr * ldp; x0[u] = q[0]; x1[u] = q[1]; x2[u] = q[2]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * m.ny;
+      if (rr >= row1) continue;
+      float y[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        float t = fmaf(w2[k], x2[u], fmaf(w1[k], x1[u], w0[k] * x0[u])) + bb[k];   // same order as the scalar kernel
+        if (scale) t = t * sc[k] + sh[k];
+        y[k] = t;
+      }
+      const size_t e = (size_t)rr * Co + m.c0;
+      if (pre) *reinterpret_cast<uint4 *>(pre + e) = pack8_bf16(y);
+      if (actout) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          if (act == VPF_ACT_RELU) y[k] = fmaxf(y[k], 0.f);
+          else if (act == VPF_ACT_GELU) y[k] = gelu_exact(y[k]);
+        }
+        *reinterpret_cast<uint4 *>(actout + e) = pack8_bf16(y);
+      }
+    }
+  }
+}
+
+// fixed-order combine of the ny row-lanes of a CTA through shared memory, then one atomic per column and CTA
+template <typename T, int NV>
+__device__ __forceinline__ void l3_cta_reduce(const L3Map &m, int Co, int CH, const T (*vals)[8], T *const *outs, T *smem) {
+  // vals[v][k]: value v of this thread's channel k; smem holds [ny][Co] of T
+  for (int v = 0; v < NV; ++v) {
+    __syncthreads();
+    for (int k = 0; k < CH; ++k) smem[m.ty * Co + m.c0 + k] = vals[v][k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < Co; c += 256) {
+      T t = 0;
+      for (int y = 0; y < m.ny; ++y) t += smem[y * Co + c];
+      atomicAdd(outs[v] + c, t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+linear3_stats_vec_kernel(const float *__restrict__ p, int ldp, const float *__restrict__ w, const float *__restrict__ b,
+                         double *__restrict__ stats, long long R, int Co, int rows_per_cta) {
+  constexpr int CH = 8, U = 4;
+  extern __shared__ double s_l3d[];   // [ny][Co]
+  const L3Map m = l3_map<CH>(Co);
+  float w0[CH], w1[CH], w2[CH], bb[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) { const int c = m.c0 + k; w0[k] = w[c * 3]; w1[k] = w[c * 3 + 1]; w2[k] = w[c * 3 + 2]; bb[k] = b[c]; }
+  double acc[2][8];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[0][k] = acc[1][k] = 0.0;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long rb = row0 + m.ty; rb < row1; rb += 16LL * U * m.ny) {   // fp32 partials over <= 64 rows, then fp64
+    float pa[CH], pq[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) pa[k] = pq[k] = 0.f;
+    const long long re = min(row1, rb + 16LL * U * m.ny);
+    for (long long r = rb; r < re; r += (long long)U * m.ny) {
+      float x0[U], x1[U], x2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * m.ny;
+        if (rr < re) { const float *q = p + (size_t)rr * ldp; x0[u] = q[0]; x1[u] = q[1]; x2[u] = q[2]; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + (long long)u * m.ny >= re) continue;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const float y = fmaf(w2[k], x2[u], fmaf(w1[k], x1[u], w0[k] * x0[u])) + bb[k];
+          pa[k] += y; pq[k] += y * y;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) { acc[0][k] += pa[k]; acc[1][k] += pq[k]; }
+  }
+  double *outs[2] = {stats, stats + Co};
+  l3_cta_reduce<double, 2>(m, Co, CH, acc, outs, s_l3d);
+}
+
+// BN(train)+ReLU backward through the recomputed y = w.p + b (see linear3_bn_bwd_kernel): 4 channels per thread
+template <int PHASE>
+__global__ void __launch_bounds__(256)
+linear3_bn_bwd_vec_kernel(const bf16 *__restrict__ dh, const float *__restrict__ p, int ldp, const float *__restrict__ w,
+                          const float *__restrict__ b, const float *__restrict__ scale, const float *__restrict__ shift,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, double *__restrict__ red,
+                          float *__restrict__ dW, float *__restrict__ db, long long R, int Co, int rows_per_cta) {
+  constexpr int CH = 4, U = 4;
+  extern __shared__ double s_l3d[];   // [ny][Co] doubles (phase 1) / floats (phase 2)
+  const L3Map m = l3_map<CH>(Co);
+  float w0[CH], w1[CH], w2[CH], bb[CH], sc[CH], sh[CH], rs[CH], nmr[CH], m1[CH], m2[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = m.c0 + k;
+    w0[k] = w[c * 3]; w1[k] = w[c * 3 + 1]; w2[k] = w[c * 3 + 2]; bb[k] = b[c];
+    sc[k] = scale[c]; sh[k] = shift[c]; rs[k] = rstd[c]; nmr[k] = mean[c];
+    m1[k] = PHASE == 2 ? (float)(red[c] / (double)R) : 0.f;
+    m2[k] = PHASE == 2 ? (float)(red[Co + c] / (double)R) : 0.f;
+  }
+  double dacc[2][8];
+  float facc[4][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { dacc[0][k] = dacc[1][k] = 0.0; facc[0][k] = facc[1][k] = facc[2][k] = facc[3][k] = 0.f; }
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long rb = row0 + m.ty; rb < row1; rb += 16LL * U * m.ny) {
+    float pa[CH], pq[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) pa[k] = pq[k] = 0.f;
+    const long long re = min(row1, rb + 16LL * U * m.ny);
+    for (long long r = rb; r < re; r += (long long)U * m.ny) {
+      float x0[U], x1[U], x2[U];
+      uint2 dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * m.ny;
+        if (rr < re) {
+          const float *q = p + (size_t)rr * ldp;
+          x0[u] = q[0]; x1[u] = q[1]; x2[u] = q[2];
+          dv[u] = __ldg(reinterpret_cast<const uint2 *>(dh + (size_t)rr * Co + m.c0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + (long long)u * m.ny >= re) continue;
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&dv[u]);
+        const float2 d01 = __bfloat1622float2(h[0]), d23 = __bfloat1622float2(h[1]);
+        const float dd[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const float y = fmaf(w2[k], x2[u], fmaf(w1[k], x1[u], w0[k] * x0[u])) + bb[k];
+          float d = dd[k];
+          if (!(y * sc[k] + sh[k] > 0.f)) d = 0.f;
+          const float xh = (y - nmr[k]) * rs[k];
+          if (PHASE == 1) { pa[k] += d; pq[k] += d * xh; }
+          else {
+            const float g = sc[k] * (d - m1[k] - xh * m2[k]);
+            facc[0][k] += g * x0[u]; facc[1][k] += g * x1[u]; facc[2][k] += g * x2[u]; facc[3][k] += g;
+          }
+        }
+      }
+    }
+    if (PHASE == 1) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) { dacc[0][k] += pa[k]; dacc[1][k] += pq[k]; }
+    }
+  }
+  if (PHASE == 1) {
+    double *outs[2] = {red, red + Co};
+    l3_cta_reduce<double, 2>(m, Co, CH, dacc, outs, s_l3d);
+  } else {
+    // dW is [Co][3]: combine per column in shared memory, then strided atomics
+    float *sf = reinterpret_cast<float *>(s_l3d);
+    for (int v = 0; v < 4; ++v) {
+      __syncthreads();
+      for (int k = 0; k < CH; ++k) sf[m.ty * Co + m.c0 + k] = facc[v][k];
+      __syncthreads();
+      for (int c = threadIdx.x; c < Co; c += 256) {
+        float t = 0.f;
+        for (int y = 0; y < m.ny; ++y) t += sf[y * Co + c];
+        if (v < 3) atomicAdd(dW + c * 3 + v, t); else atomicAdd(db + c, t);
+      }
+    }
+  }
+}
+
+// dW[c][j] += sum_r dy[r,c] p[r,j];  db[c] += sum_r dy[r,c]   (dy bf16, 8 channels per thread)
+__global__ void __launch_bounds__(256)
+linear3_bwd_vec_kernel(const bf16 *__restrict__ dy, const float *__restrict__ p, int ldp, float *__restrict__ dW,
+                       float *__restrict__ db, long long R, int Co, int rows_per_cta) {
+  constexpr int CH = 8, U = 4;
+  extern __shared__ double s_l3d[];
+  const L3Map m = l3_map<CH>(Co);
+  float facc[4][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) facc[0][k] = facc[1][k] = facc[2][k] = facc[3][k] = 0.f;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
+  for (long long r = row0 + m.ty; r < row1; r += (long long)U * m.ny) {
+    float x0[U], x1[U], x2[U];
+    uint4 dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * m.ny;
+      if (rr < row1) {
+        const float *q = p + (size_t)rr * ldp;
+        x0[u] = q[0]; x1[u] = q[1]; x2[u] = q[2];
+        dv[u] = __ldg(reinterpret_cast<const uint4 *>(dy + (size_t)rr * Co + m.c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + (long long)u * m.ny >= row1) continue;
+      float d[8];
+      unpack8_bf16(dv[u], d);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        facc[0][k] += d[k] * x0[u]; facc[1][k] += d[k] * x1[u]; facc[2][k] += d[k] * x2[u]; facc[3][k] += d[k];
+      }
+    }
+  }
+  float *sf = reinterpret_cast<float *>(s_l3d);
+  for (int v = 0; v < 4; ++v) {
+    __syncthreads();
+    for (int k = 0; k < CH; ++k) sf[m.ty * Co + m.c0 + k] = facc[v][k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < Co; c += 256) {
+      float t = 0.f;
+      for (int y = 0; y < m.ny; ++y) t += sf[y * Co + c];
+      if (v < 3) atomicAdd(dW + c * 3 + v, t); else atomicAdd(db + c, t);
+    }
+  }
+}
+
 __global__ void bn_param_grad_kernel(const double *__restrict__ red, float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
@@ -305,6 +573,12 @@ int vpf_linear3_fwd(const float *p, int ldp, const float *w, const float *b, con
   VPF_REQUIRE((scale == nullptr) == (shift == nullptr), "linear3_fwd: scale/shift must come together");
   VPF_REQUIRE(Co % 8 == 0, "linear3_fwd: Co=%d must be a multiple of 8", Co);
   if (R == 0) return VPF_OK;
+  if (l3_vec_ok(Co, 8)) {
+    const int ny = 256 / (Co / 8);
+    const int rpc = (int)max((long long)ny * 4, ceil_div(R, (long long)num_sms() * 8));
+    linear3_fwd_vec_kernel<<<(unsigned)ceil_div(R, (long long)rpc), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, scale, shift, (bf16 *)pre_bf16, (bf16 *)act_bf16, act, R, Co, rpc);
+    return check_launch("linear3_fwd_vec_kernel");
+  }
   linear3_fwd_kernel<<<grid_for((size_t)R * Co / 8), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, scale, shift, (bf16 *)pre_bf16, (bf16 *)act_bf16, act, R, Co);
   return check_launch("linear3_fwd_kernel");
 }
@@ -313,6 +587,12 @@ int vpf_linear3_stats(const float *p, int ldp, const float *w, const float *b, d
   VPF_REQUIRE(p && w && b && stats, "linear3_stats: null pointer");
   if (R == 0) return VPF_OK;
   const int rpc = rows_per_cta_for(R);
+  if (l3_vec_ok(Co, 8)) {
+    const int smem = (256 / (Co / 8)) * Co * (int)sizeof(double);
+    VPF_REQUIRE(smem <= 48 * 1024, "linear3_stats: Co=%d too wide", Co);
+    linear3_stats_vec_kernel<<<(unsigned)ceil_div(R, (long long)rpc), 256, smem, (cudaStream_t)stream>>>(p, ldp, w, b, stats, R, Co, rpc);
+    return check_launch("linear3_stats_vec_kernel");
+  }
   linear3_stats_kernel<<<(unsigned)ceil_div(R, (long long)rpc), 256, 0, (cudaStream_t)stream>>>(p, ldp, w, b, stats, R, Co, rpc);
   return check_launch("linear3_stats_kernel");
 }
@@ -322,6 +602,11 @@ int vpf_linear3_bwd(const void *dy, int dy_bf16, const float *p, int ldp, float 
   if (R == 0) return VPF_OK;
   const int rpc = rows_per_cta_for(R);
   const unsigned grid = (unsigned)ceil_div(R, (long long)rpc);
+  if (dy_bf16 && l3_vec_ok(Co, 8) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int smem = (256 / (Co / 8)) * Co * (int)sizeof(float);
+    linear3_bwd_vec_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16 *)dy, p, ldp, dW, db, R, Co, rpc);
+    return check_launch("linear3_bwd_vec_kernel");
+  }
   if (dy_bf16) linear3_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, p, ldp, dW, db, R, Co, rpc);
   else linear3_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)dy, p, ldp, dW, db, R, Co, rpc);
   return check_launch("linear3_bwd_kernel");
@@ -336,10 +621,18 @@ int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float
   VPF_CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * Co, st));
   const int rpc = rows_per_cta_for(R);
   const unsigned grid = (unsigned)ceil_div(R, (long long)rpc);
-  linear3_bn_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
-  VPF_TRY(check_launch("linear3_bn_bwd_kernel<1>"));
-  linear3_bn_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
-  VPF_TRY(check_launch("linear3_bn_bwd_kernel<2>"));
+  if (l3_vec_ok(Co, 4) && (reinterpret_cast<uintptr_t>(dh_bf16) & 7) == 0 && (256 / (Co / 4)) * Co * 8 <= 48 * 1024) {
+    const int smem = (256 / (Co / 4)) * Co * (int)sizeof(double);
+    linear3_bn_bwd_vec_kernel<1><<<grid, 256, smem, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+    VPF_TRY(check_launch("linear3_bn_bwd_vec_kernel<1>"));
+    linear3_bn_bwd_vec_kernel<2><<<grid, 256, smem, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+    VPF_TRY(check_launch("linear3_bn_bwd_vec_kernel<2>"));
+  } else {
+    linear3_bn_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+    VPF_TRY(check_launch("linear3_bn_bwd_kernel<1>"));
+    linear3_bn_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16 *)dh_bf16, p, ldp, w, b, scale, shift, mean, rstd, red, dW, db, R, Co, rpc);
+    VPF_TRY(check_launch("linear3_bn_bwd_kernel<2>"));
+  }
   bn_param_grad_kernel<<<ceil_div(Co, 128), 128, 0, st>>>(red, dgamma, dbeta, Co);
   return check_launch("bn_param_grad_kernel");
 }
