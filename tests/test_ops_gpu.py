@@ -274,6 +274,9 @@ def test_patchify_and_misc():
     out = ops.patchify(img, 12)
     ref = rearrange(img, "b (h p1) (w p2) c -> (b h w) (p1 p2 c)", p1=12, p2=12)
     assert torch.equal(out.float(), ref.to(BF16).float())
+    # NCHW source (what the data loader yields before pretrain.py:179 permutes it): same patches, bit for bit
+    out2 = ops.patchify(img.permute(0, 3, 1, 2).contiguous(), 12, nchw=True)
+    assert torch.equal(out2, out)
     a, b = rnd(1000, 2), rnd(1000, 3)
     close(ops.add_scale(a, b, 0.5), 0.5 * (a + b))
     close(ops.cast_bf16(a), a, bf16=True)

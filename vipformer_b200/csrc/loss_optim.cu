@@ -38,7 +38,7 @@ __device__ __forceinline__ void self_pos(int i, int b_local, int col_offset, int
 // ---- tiled fp32 SIMT GEMM for the similarity matrix and its backward (sizes are tiny: 2b x 2bW x D).  fp32 on purpose:
 // logits are divided by T = 0.1, bf16 operands would put ~1e-2 of noise on them.
 //   b_nt = 1: C[M,N] = alpha * A[M,K] . B[N,K]^T        b_nt = 0: C[M,N] = alpha * A[M,K] . B[K,N]
-constexpr int kSgTile = 64, kSgK = 16;
+constexpr int kSgTile = 64, kSgK = 64;   // K slab of 64: 4x fewer load -> sync -> FMA -> sync rounds than 16 (the kernel is latency bound: 32-64 CTAs)
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K,
              float alpha, int b_nt) {
