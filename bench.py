@@ -316,7 +316,7 @@ def gemm_roofline(eng, load, pk, pk_kind):
     ach = fl / t / 1e12
     peak = pk["bf16_tflops_sustained"]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 254 GEMM launches of one step at
-    # 256 pairs/GPU: profiles/r01_step_launches_v5.csv (ncu, one capture: 27.3 GB read + 6.8 GB written); algorithmic = operands + result
+    # 256 pairs/GPU: profiles/r01_step_launches_v6.csv (ncu, one capture: 27.3 GB read + 6.8 GB written); algorithmic = operands + result
     traffic = 134.0e6 if eng.b == 256 else None
     return {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA)", "bound": "tensor", "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "peak_kind": pk_kind + " sustained (kernel timed inside a long step)",
