@@ -221,9 +221,13 @@ def run_ours(args):
     else:
         # input pipeline as a DataLoader with pinned memory + prefetch provides it: the H2D copy of step i+1 runs on a
         # copy stream while step i computes; every step's inputs are copied (and its losses read back) inside the timed region
+        # The losses of step i are read on the host while step i+1 runs (one-step lag, as a loop that logs the
+        # previous iteration's loss.item() does); the last step's are read before the clock stops.
         eng.prefetch_host(*host[0])
         for i in range(args.steps):
-            eng.step_host_prefetched(host[(i + 1) % len(host)] if i + 1 < args.steps else None)
+            eng.step_host_prefetched(host[(i + 1) % len(host)] if i + 1 < args.steps else None, lag_losses=True)
+        last = eng.drain_losses()
+        assert last is not None and bool(torch.isfinite(last).all())
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -255,7 +259,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": b, "global_pairs": b * world, "points": cfg["N"],
                        "parallelism": f"dp{world}", "negatives": "global (all-gather)" if eng.gather else "rank-local",
-                       "two_stream_branches": eng.side is not None, "e2e_input": "synchronous" if args.e2e_sync else "H2D of step i+1 prefetched on a copy stream during step i", "cuda_graph": eng.graph is not None, "dropout": "atten 0.1 / mlp 0.5",
+                       "two_stream_branches": eng.side is not None, "e2e_input": "synchronous" if args.e2e_sync else "H2D of step i+1 prefetched on a copy stream during step i; losses of step i read back (D2H) while step i+1 runs, the last before the clock stops", "cuda_graph": eng.graph is not None, "dropout": "atten 0.1 / mlp 0.5",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 2 alternating input batches"},
             "e2e": {"value": e2e_value, "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps * 2),

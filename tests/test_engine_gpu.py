@@ -94,5 +94,15 @@ def test_engine_prefetched_host_steps_match_synchronous():
             for k in range(3):
                 out.append(eng.step_host_prefetched(batches[k + 1] if k + 1 < 3 else None).clone())
         runs.append(torch.stack(out))
+    # lagged loss read-back: call k returns the losses of step k-1, drain_losses() the last
+    torch.manual_seed(0)
+    eng, *_ = _engine(False, seed=5, lr=0.0)
+    eng.prefetch_host(*batches[0])
+    lagged = [eng.step_host_prefetched(batches[k + 1] if k + 1 < 3 else None, lag_losses=True) for k in range(3)]
+    assert lagged[0] is None
+    lagged = [t.clone() for t in lagged[1:]] + [eng.drain_losses().clone()]
+    assert eng.drain_losses() is None
+    runs.append(torch.stack(lagged))
     assert torch.allclose(runs[0], runs[1], rtol=1e-5, atol=1e-5), runs
+    assert torch.allclose(runs[0], runs[2], rtol=1e-5, atol=1e-5), runs
     assert not torch.allclose(runs[0][0], runs[0][1], rtol=1e-3, atol=1e-3)   # the batches do differ

@@ -74,6 +74,7 @@ class PretrainEngine:
         self.graph = None
         self.side = torch.cuda.Stream(device=self.device) if overlap_branches else None
         self._copy_stream, self._staged = None, False
+        self._loss_ring, self._loss_pending = None, None
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------ one step
@@ -161,9 +162,14 @@ class PretrainEngine:
             self._stage_ready.record(cs)
         self._staged = True
 
-    def step_host_prefetched(self, next_batch=None):
+    def step_host_prefetched(self, next_batch=None, lag_losses=False):
         """One step on the batch staged by prefetch_host(); starts the copy of `next_batch` (a (pc_t1, pc_t2, imgs)
-        tuple of pinned host tensors) before the step is launched, then reads the losses back (synchronises)."""
+        tuple of pinned host tensors) before the step is launched, then reads the losses back (synchronises).
+
+        lag_losses=True: the device-to-host copy of this step's losses is only enqueued; the call returns the losses
+        of the PREVIOUS step (None on the first call) once their copy has landed, so the launching thread can run one
+        step ahead of the GPU -- what a training loop that logs `loss.item()` of the previous iteration does.
+        drain_losses() returns the last step's."""
         if not self._staged:
             raise RuntimeError("step_host_prefetched: no staged batch; call prefetch_host() first")
         cur = torch.cuda.current_stream()
@@ -175,9 +181,28 @@ class PretrainEngine:
         if next_batch is not None:
             self.prefetch_host(*next_batch)
         self.step()
-        self.losses_host.copy_(self.losses, non_blocking=True)
-        cur.synchronize()
-        return self.losses_host
+        if not lag_losses:
+            self.losses_host.copy_(self.losses, non_blocking=True)
+            cur.synchronize()
+            return self.losses_host
+        if self._loss_ring is None:
+            self._loss_ring = [(torch.zeros(3, dtype=F32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+        buf, ev = self._loss_ring[self.steps_done & 1]
+        buf.copy_(self.losses, non_blocking=True)
+        ev.record(cur)
+        prev, self._loss_pending = self._loss_pending, (buf, ev)
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        return prev[0].clone()            # the ring slot is reused two steps later
+
+    def drain_losses(self):
+        """Losses of the last lag_losses step (waits for their device-to-host copy)."""
+        prev, self._loss_pending = self._loss_pending, None
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        return prev[0].clone()
 
     def step_host(self, pc_t1, pc_t2, imgs):
         """End-to-end step from (pinned) HOST tensors: H2D copies, the step, D2H read of the losses (synchronises).
