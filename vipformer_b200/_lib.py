@@ -54,9 +54,14 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Raw handle of torch's current CUDA stream on the current device.  Called once per kernel launch, so it uses the
+    two C entry points underneath torch.cuda.current_stream() (7 us -> well under 1 us per call)."""
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:      # private names moved: the public (slower) route
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def launch_count():

@@ -31,6 +31,10 @@ class Arena:
 
     # ------------------------------------------------------------------ parameters
     def ensure(self, device):
+        # An engine-managed arena was laid out (and verified) when the engine was built and nothing re-points parameter
+        # storage afterwards: skip the per-call walk over the module tree (it was > 50 % of the host time of a step).
+        if self.managed and self.flat_p is not None and self.flat_p.device == device:
+            return
         ps = self.params()
         ok = self.flat_p is not None and self.flat_p.device == device and len(ps) == len(self._offsets)
         if ok:
@@ -57,9 +61,9 @@ class Arena:
         self.gen += 1
 
     def refresh_shadows(self, force=False):
-        ps = self.params()
         if self.managed and not force and self._versions is not None:
             return
+        ps = self.params()
         vers = [p._version for p in ps]
         if not force and vers == self._versions:
             return
@@ -70,6 +74,8 @@ class Arena:
 
     # ------------------------------------------------------------------ gradients
     def ensure_grads(self):
+        if self.managed and self.flat_g is not None:
+            return
         ps = self.params()
         ok = self.flat_g is not None
         if ok:
