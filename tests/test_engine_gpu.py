@@ -29,7 +29,7 @@ def test_engine_steps_train(graph):
     assert not torch.equal(p0, eng.arena.flat_p)
     # bf16 shadows track the fp32 masters after every fused AdamW step
     assert torch.equal(eng.arena.flat_bf.float(), eng.arena.flat_p.to(torch.bfloat16).float())
-    assert eng.state[0].item() == eng.steps_done
+    assert eng.state[0].item() == eng.steps_done == 8     # graph warm-up does not train (one step per batch)
     # parameters are views of the arena; gradients too
     p = next(eng.pc_model.parameters())
     assert p.data_ptr() == eng.arena.flat_p.data_ptr() and p.grad.data_ptr() == eng.arena.flat_g.data_ptr()

@@ -21,6 +21,21 @@ from .loss import pretrain_loss
 F32 = torch.float32
 
 
+def allreduce_gradients(root, op=None):
+    """DDP's job for a hand-written loop around the mirror modules (pretrain.py:104-105): average the flat gradient
+    buffer of `root`'s parameter arena over the ranks with ONE NCCL all-reduce.  torch's DistributedDataParallel cannot
+    wrap the mirror: the block Functions write parameter gradients straight into the arena (p.grad views), so DDP's
+    per-parameter autograd hooks never fire.  Call between loss.backward() and optimizer.step()."""
+    import torch.distributed as dist
+
+    arena = params.arena_of(root)
+    if arena.flat_g is None:
+        raise RuntimeError("no gradients yet: call after backward()")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(arena.flat_g, op=dist.ReduceOp.AVG if op is None else op)
+    return arena.flat_g
+
+
 class PretrainEngine:
     def __init__(self, pc_model, img_model, *, batch_pairs, num_points, img_size=144, lr=1e-3, betas=(0.9, 0.999),
                  eps=1e-8, weight_decay=1e-2, temperature=0.1, cmid_weight=1.0, gather_distributed=None,
@@ -110,13 +125,32 @@ class PretrainEngine:
                   self.betas[0], self.betas[1], self.eps, self.weight_decay)   # pretrain.py:210
         ops.add_scale(losses.detach(), None, 1.0, out=self.losses)
 
+    def _snapshot(self):
+        """Everything a step mutates besides the activations: parameters, Adam moments, step/seed state, BatchNorm
+        buffers, the FPS-start generator."""
+        return ([t.clone() for t in (self.arena.flat_p, self.arena.flat_bf, self.m, self.v, self.state)],
+                [b.clone() for b in self.root.buffers()], self.gen.get_state())
+
+    def _restore(self, snap):
+        tensors, bufs, gstate = snap
+        for dst, src in zip((self.arena.flat_p, self.arena.flat_bf, self.m, self.v, self.state), tensors):
+            dst.copy_(src)
+        for dst, src in zip(self.root.buffers(), bufs):
+            dst.copy_(src)
+        self.gen.set_state(gstate)
+
     def _capture(self):
+        # Warm-up outside capture (allocator pools, lazy module init, NCCL) must not train: the reference takes exactly
+        # one optimizer step per batch (pretrain.py:209-211).  Snapshot, run the body twice, put everything back.
+        snap = self._snapshot()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(2):                            # warm-up outside capture (allocator, lazy init, NCCL)
+            for _ in range(2):
                 self._step_body()
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self.gen_state_registered = False
@@ -126,7 +160,6 @@ class PretrainEngine:
             pass
         with torch.cuda.graph(self.graph):
             self._step_body()
-        self.steps_done += 2
 
     def step(self):
         """Run one optimisation step on whatever is in self.pc_in / self.img_in; returns the device tensor

@@ -173,6 +173,8 @@ def group2emb_fwd(nb, W, bn, cfg, training, save=True):
 
 def group2emb_bwd(dtok, c, W, G, cfg):
     Gt, S, D = cfg.Gt, cfg.S, cfg.D
+    if not c.st1.training:
+        raise NotImplementedError("backward through an eval-mode Group2Emb (running-statistics BatchNorm) is not built")
     R = Gt * S
     ops.colsum(dtok, sum32=G.b4)
     dy4 = ops.group_max_bwd(dtok, c.am4, Gt, S, D)

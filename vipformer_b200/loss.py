@@ -63,17 +63,21 @@ class _NTXentCore:
             zc, col_offset, half = z, 0, b
         loss = ops.zeros_(torch.empty(1, dtype=F32, device=x.device))
         lse, S = ops.ntxent_fwd(z, zc, b, col_offset, half, temperature, loss)
-        return loss, (z, norm, zc, lse, b, col_offset, half, temperature, dist, S)
+        return loss, [z, norm, zc, lse, b, col_offset, half, temperature, dist, S]
 
     @staticmethod
     def bwd(saved, gscale, upstream=None):
         z, norm, zc, lse, b, col_offset, half, temperature, dist, S = saved
+        if S is None:
+            raise RuntimeError("NT-Xent backward ran twice on one forward: its logits scratch is overwritten in place by "
+                               "the first backward (retain_graph=True is not supported by this fused loss)")
         if dist is not None:
             lse_all = torch.empty(2 * half, dtype=F32, device=z.device)
             dist.all_gather_into_tensor(lse_all[:half], lse[:b].contiguous())
             dist.all_gather_into_tensor(lse_all[half:], lse[b:].contiguous())
         else:
             lse_all = lse
+        saved[-1] = None
         # DDP averages parameter gradients over ranks, so the per-rank seed stays 1/(2b) for any world size
         return ops.ntxent_bwd(z, norm, zc, lse_all, S, b, col_offset, half, temperature, gscale / (2 * b), upstream)
 

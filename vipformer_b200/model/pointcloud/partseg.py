@@ -27,6 +27,7 @@ from .utils import Group2Emb, PointNetFeaturePropagation, Sequential, divide_pat
 BF16, F32 = torch.bfloat16, torch.float32
 
 
+from ... import runtime as _rt
 from ...runtime import (StepState as _StepState, advance_dropout_seed, anchor as _anchor, as_f32_2d as _as_f32_2d,  # noqa: F401,E501
                         bump as _bump, fragment_error as _fragment_error, manual_seed, root_prepare as _root_prepare,
                         set_root as _set_root)
@@ -125,6 +126,10 @@ class _LayerBase(Sequential):
     _op_counter = 0
 
     def _init_op_base(self):
+        if self._D // self._H != 64:
+            # the attention kernels are built for head_dim 64 (every published ViPFormer config: D256/H4, D384/H6)
+            raise NotImplementedError(f"head dim {self._D // self._H} (= num_latent_channels / num_heads) is not built; "
+                                      "the sm_100a attention kernels are specialised for 64")
         _LayerBase._op_counter += 8
         self._op_base = _LayerBase._op_counter
 
@@ -251,6 +256,8 @@ class _EncoderFn(torch.autograd.Function):
         seed = _StepState.seed_ptr(x_q.device)
         ctxs = []
         ca = enc.cross_attn_1
+        training = (ca is not None and ca.training) or any(l.training for l in enc.sa_layers)
+        off = _rt.next_op_offset(arena.managed) if training else 0
         if ca is not None:
             Lk = kv.shape[1]
             kv2 = kv.reshape(-1, D)
@@ -258,12 +265,12 @@ class _EncoderFn(torch.autograd.Function):
                 kv2 = kv2.float()
             kv2 = kv2.contiguous()
             cfg = ca._cfg(B, L, Lk)
-            x, c = Fn.ca_layer_fwd(x, pos2, kv2, ca._weights(), cfg, seed, ca._op_base, save)
-            ctxs.append((ca, cfg, c))
+            x, c = Fn.ca_layer_fwd(x, pos2, kv2, ca._weights(), cfg, seed, ca._op_base + off, save)
+            ctxs.append((ca, cfg, c, ca._op_base + off))
         for layer in enc.sa_layers:
             cfg = layer._cfg(B, L)
-            x, c = Fn.sa_layer_fwd(x, pos2, layer._weights(), cfg, seed, layer._op_base, save)
-            ctxs.append((layer, cfg, c))
+            x, c = Fn.sa_layer_fwd(x, pos2, layer._weights(), cfg, seed, layer._op_base + off, save)
+            ctxs.append((layer, cfg, c, layer._op_base + off))
         if save:
             ctx.ctxs, ctx.arena, ctx.has_pos = ctxs, arena, pos2 is not None
             ctx.pos_shape = None if pos is None else pos.shape
@@ -281,11 +288,11 @@ class _EncoderFn(torch.autograd.Function):
         if ctx.has_pos:
             dpos = ops.zeros_(torch.empty(ctx.pos_shape, dtype=F32, device=dout.device))
         dkv = None
-        for layer, cfg, c in reversed(ctx.ctxs):
+        for layer, cfg, c, op_base in reversed(ctx.ctxs):
             if isinstance(layer, CrossAttentionLayer):
-                dx, dkv = Fn.ca_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, layer._op_base, dpos)
+                dx, dkv = Fn.ca_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, op_base, dpos)
             else:
-                dx = Fn.sa_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, layer._op_base, dpos)
+                dx = Fn.sa_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, op_base, dpos)
         ctx.ctxs = None
         if dkv is not None:
             dkv = dkv.view(ctx.kv_shape)

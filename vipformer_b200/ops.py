@@ -171,14 +171,14 @@ def colsum(x, *, sum64=None, sumsq64=None, sum32=None):
 
 class BNState:
     """Folded affine + saved statistics of one BatchNorm1d call."""
-    __slots__ = ("scale", "shift", "mean", "rstd", "R")
+    __slots__ = ("scale", "shift", "mean", "rstd", "R", "training")
 
 
 def bn_stats_finalize(stats, R, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5):
     C = gamma.numel()
     st = BNState()
     buf = torch.empty((4, C), dtype=F32, device=gamma.device)
-    st.scale, st.shift, st.mean, st.rstd, st.R = buf[0], buf[1], buf[2], buf[3], R
+    st.scale, st.shift, st.mean, st.rstd, st.R, st.training = buf[0], buf[1], buf[2], buf[3], R, bool(training)
     _lib.call("vpf_bn_finalize", _p(stats), _ll(R), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
               _f(momentum), _f(eps), _i(int(training)), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd), _i(C), _s())
     return st
@@ -197,6 +197,11 @@ def bn_forward(x, gamma, beta, running_mean, running_var, training, relu, out_dt
 
 
 def bn_backward(dy, x, st, relu, dgamma, dbeta, out_dtype=BF16):
+    if not st.training:
+        # vpf_bn_bwd applies the batch-statistics gradient (mean / projection terms); a forward that normalised with the
+        # running statistics (module.eval()) has a different Jacobian.  Every reference script trains with BN in train mode.
+        raise NotImplementedError("backward through an eval-mode BatchNorm1d (running statistics) is not built; "
+                                  "call .train() on the module before a forward you backpropagate through")
     R, C = x.shape
     red = torch.empty(3 * C, dtype=torch.float64, device=x.device)
     dx = torch.empty((R, C), dtype=out_dtype, device=x.device)

@@ -33,6 +33,34 @@ class StepState:
         ops.step_advance(cls.get(device))
 
 
+# ---- per-forward dropout epoch (drop-in path, no engine) ---------------------------------------------------------
+# Dropout masks are keep(e) = hash(seed, op_id, element).  PretrainEngine advances the device-resident seed once per
+# step.  On the plain drop-in path (model(x); loss.backward(); optimizer.step()) nobody does, so every training-mode
+# encoder forward folds a host-side epoch counter into the op ids instead: consecutive forwards draw different masks
+# (nn.Dropout semantics, partseg.py:81,208-213) and the backward pass, which reads the op ids saved at forward time,
+# regenerates exactly the forward's masks.
+_EPOCH = [0]
+EPOCH_STRIDE = 1 << 12
+
+
+def next_op_offset(managed):
+    """Offset added to a layer's dropout op ids for this forward call (0 under an engine-managed arena, whose seed
+    advances on the device so that a captured CUDA graph stays valid)."""
+    if managed:
+        return 0
+    _EPOCH[0] = (_EPOCH[0] + 1) & 0xFFFFF
+    return _EPOCH[0] * EPOCH_STRIDE
+
+
+# ---- test tap: when set to a dict, block forwards drop their saved context here (discrete choices for parity tests)
+TAP = None
+
+
+def tap(name, value):
+    if TAP is not None:
+        TAP.setdefault(name, []).append(value)
+
+
 def _dev(device):
     return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
