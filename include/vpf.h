@@ -230,13 +230,19 @@ int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long 
 /* ------------------------------------------------------------------ loss + optimiser
  * NT-Xent (lightly 1.1.21 NTXentLoss; call sites pretrain.py:155,196,202). */
 int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *stream);
-/* S_ws: fp32 scratch [n_r, n_c] -- holds the logits after fwd (keep it for bwd, which overwrites it); G_ws [n_r, D]. */
+/* Rows = this rank's 2*b_local normalised embeddings zr (out0 rows, then out1 rows); columns = n_c embeddings of all
+ * ranks.  Local row i < b_local sits at column col_offset + i and its positive at col_offset + half + i (and vice versa
+ * for i >= b_local).  Column j lives at row (j / zc_blk) * zc_ld + zc_base + j % zc_blk of zc (and of lse_all): with
+ * every rank's PACKED block [imid rows | cmid rows] all-gathered once, zc_blk = 2b, zc_ld = 4b and zc_base selects the
+ * loss term; a plain [n_c, D] buffer is zc_blk = zc_ld = n_c, zc_base = 0.
+ * S_ws: fp32 scratch [n_r, n_c] -- holds the logits after fwd (keep it for bwd, which overwrites it); G_ws [n_r, D]. */
 int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local,
-                   int col_offset, int half, float temperature, float *S_ws, float *lse_out,
-                   float *loss_out, void *stream);
+                   int col_offset, int half, int zc_blk, int zc_ld, int zc_base, float temperature,
+                   float *S_ws, float *lse_out, float *loss_out, void *stream);
 int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all,
-                   int n_c, int D, int b_local, int col_offset, int half, float temperature,
-                   float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream);
+                   int n_c, int D, int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base,
+                   float temperature, float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx,
+                   void *stream);
 /* torch.optim.AdamW step (pretrain.py:121-124,210) on a flat buffer, refreshing the bf16 shadow. */
 int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n,
               const float *lr_ptr, float beta1, float beta2, float eps, float weight_decay,

@@ -28,27 +28,23 @@ def _worker(rank, world, port, ret):
     z = x / norm[:, None]
     # all-gather exactly as _NTXentCore.fwd lays it out
     col_offset, half = shard_layout(rank, world, B)
-    zc = torch.empty((2 * half, D), dtype=torch.float64)
-    parts0 = [torch.empty((B, D), dtype=torch.float64) for _ in range(world)]
-    parts1 = [torch.empty((B, D), dtype=torch.float64) for _ in range(world)]
-    dist.all_gather(parts0, z[:B].contiguous())
-    dist.all_gather(parts1, z[B:].contiguous())
-    zc[:half], zc[half:] = torch.cat(parts0), torch.cat(parts1)
+    n_c = 2 * B * world
+    parts = [torch.empty((2 * B, D), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, z.contiguous())          # ONE all-gather of the stacked [out0; out1] rows: rank-major columns
+    zc = torch.cat(parts)
     s = z @ zc.t() / T
     lse = torch.empty(2 * B, dtype=torch.float64)
     loss = 0.0
     for i in range(2 * B):
         me, pos = self_pos_columns(i, B, col_offset, half)
-        mask = torch.ones(2 * half, dtype=torch.bool)
+        mask = torch.ones(n_c, dtype=torch.bool)
         mask[me] = False
         lse[i] = torch.logsumexp(s[i][mask], 0)
         loss += (lse[i] - s[i, pos]) / (2 * B)
     # backward: all-gather of the per-row LSE, then each rank alone computes d(sum over ALL rows)/d z_k for its rows
-    l0 = [torch.empty(B, dtype=torch.float64) for _ in range(world)]
-    l1 = [torch.empty(B, dtype=torch.float64) for _ in range(world)]
-    dist.all_gather(l0, lse[:B].contiguous())
-    dist.all_gather(l1, lse[B:].contiguous())
-    lse_all = torch.cat([torch.cat(l0), torch.cat(l1)])
+    ls = [torch.empty(2 * B, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(ls, lse.contiguous())           # ONE all-gather, same rank-major layout as the columns
+    lse_all = torch.cat(ls)
     gscale = 1.0 / (2 * B)          # stays 1/(2b): the gradient all-reduce AVERAGES over ranks
     dx = torch.empty_like(x)
     for k in range(2 * B):
@@ -90,7 +86,7 @@ def test_shard_layout_covers_every_column_once():
         seen = set()
         for r in range(world):
             off, half = shard_layout(r, world, B)
-            assert half == world * B
+            assert half == B and off == 2 * r * B
             for i in range(2 * B):
                 me, pos = self_pos_columns(i, B, off, half)
                 assert abs(me - pos) == half and me not in seen

@@ -106,3 +106,92 @@ def test_engine_prefetched_host_steps_match_synchronous():
     assert torch.allclose(runs[0], runs[1], rtol=1e-5, atol=1e-5), runs
     assert torch.allclose(runs[0], runs[2], rtol=1e-5, atol=1e-5), runs
     assert not torch.allclose(runs[0][0], runs[0][1], rtol=1e-3, atol=1e-3)   # the batches do differ
+
+
+def test_engine_step_matches_oracle_fwd_bwd_adamw():
+    """One engine step (dropout ON, eager) against the oracle: forward + both NT-Xent terms + backward with the product's
+    discrete choices pinned and its dropout masks injected, then torch.optim.AdamW (pretrain.py:121-124,209-211).
+    Adam's first step is p -= lr * (g / (|g| + eps) + wd * p): the update is +-lr wherever |g| >> eps, so parameters are
+    compared through (i) the first moment m = 0.1 g (rel-Frobenius <= 5e-2 per tensor: the gradient gate) and (ii) the
+    sign agreement / cosine of the parameter deltas."""
+    import os
+
+    import numpy as np
+
+    import vipformer_b200.runtime as rt
+    from test_oracle_model_golden import oracle_run
+    from test_parity_pinned_gpu import op_bases, pins_from_tap, relfro
+    from vipformer_b200.engine import PretrainEngine
+
+    cfg = _synth.MODEL_CASES["small"]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    o0 = oracle_run(cfg)
+    pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)
+    pc.load_state_dict({k: v.detach() for k, v in o0["sd_pc"].items() if k in pc.state_dict()})
+    im.load_state_dict({k: v.detach() for k, v in o0["sd_im"].items() if k in im.state_dict()})
+    eng = PretrainEngine(pc, im, batch_pairs=cfg["b"], num_points=cfg["N"], lr=1e-3, use_cuda_graph=False, seed=9)
+    pts, _, imgs = o0["inputs"]
+    eng.pc_in.copy_(pts.cuda())
+    eng.img_in.copy_(imgs.cuda().permute(0, 3, 1, 2))
+    p_old = {k: v.detach().clone().cpu() for m in (("pc", eng.pc_model), ("img", eng.img_model)) for k, v in
+             ((m[0] + "." + n, p) for n, p in m[1].named_parameters())}
+    rt.TAP = {}
+    try:
+        losses = eng.step().cpu().numpy()
+        tap = rt.TAP
+    finally:
+        rt.TAP = None
+    torch.cuda.synchronize()
+    seed = int(eng.state[1].item())
+    pins = pins_from_tap(tap, cfg)
+    drop = dict(seed=seed, op_bases=op_bases(eng.pc_model, eng.img_model), atten_drop=0.1, mlp_drop=0.5)
+    o = oracle_run(cfg, pins=pins, drop=drop, start=eng.start.cpu().numpy())
+    assert np.all(np.abs(losses - np.array(o["loss"])) <= 5e-2), (losses, o["loss"])
+    leaves = [o["sd_pc"][k] for k in o["pnames"]] + [o["sd_im"][k] for k in o["inames"]]
+    grads = {("pc." + k): o["sd_pc"][k].grad.clone() for k in o["pnames"]}
+    grads.update({("img." + k): o["sd_im"][k].grad.clone() for k in o["inames"]})
+    opt = torch.optim.AdamW(leaves, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    opt.step()
+    new_ref = {("pc." + k): o["sd_pc"][k].detach() for k in o["pnames"]}
+    new_ref.update({("img." + k): o["sd_im"][k].detach() for k in o["inames"]})
+    # engine first moments, per parameter (arena order = root.parameters() order)
+    names = ["pc." + n for n, _ in eng.pc_model.named_parameters()] + ["img." + n for n, _ in eng.img_model.named_parameters()]
+    plist = list(eng.pc_model.parameters()) + list(eng.img_model.parameters())
+    assert [id(p) for p in plist] == [id(p) for p in eng.arena.params()]
+    gmax = max(g.norm().item() for g in grads.values())
+    bad, agree_n, agree_d = [], 0, 0
+    for n, p, off in zip(names, plist, eng.arena._offsets):
+        g = grads[n]
+        if g.norm().item() < 1e-4 * gmax:
+            continue
+        m_eng = eng.m[off:off + p.numel()].view(p.shape).cpu()
+        e = relfro(m_eng, 0.1 * g)
+        if e > 5e-2:
+            bad.append((n, round(e, 4)))
+        d_eng = (p.detach().cpu() - p_old[n]).reshape(-1)
+        d_ref = (new_ref[n] - p_old[n]).reshape(-1)
+        big = g.reshape(-1).abs() > 0.05 * g.abs().mean()
+        agree_n += int((torch.sign(d_eng[big]) == torch.sign(d_ref[big])).sum())
+        agree_d += int(big.sum())
+        cos = torch.nn.functional.cosine_similarity(d_eng.double().view(1, -1), d_ref.double().view(1, -1)).item()
+        if cos < 0.93:
+            bad.append((n, "delta cos", round(cos, 4)))
+    assert not bad, bad
+    assert agree_n / agree_d > 0.985, agree_n / agree_d
+
+
+def test_multi_gpu_equivalence_over_nccl():
+    """N-rank == single process on the concatenated batch (loss, feature gradients), parameters stay bit-identical across
+    ranks, eager == graph: tests/mp_equiv.py under torchrun, when the box has >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(root, "tests", "mp_equiv.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_EQUIV_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

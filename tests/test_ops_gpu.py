@@ -341,6 +341,50 @@ def test_ntxent_global_negatives_matches_single_process():
         close(dx[b:], xr1.grad[r * b:(r + 1) * b], tol=1e-3)
 
 
+def test_ntxent_packed_rank_major_layout_matches_single_process():
+    """The layout loss.py uses across ranks: every 'rank' contributes ONE packed block [term0: out0,out1 | term1: out0,out1]
+    to the gathered buffer, logits columns are found through the column map (blk = 2b, ld = 4b, base = term * 2b), the
+    row log-sum-exps are gathered in the same packed layout.  Both terms must reproduce the single-process loss/gradient."""
+    from vipformer_b200 import ops
+    from vipformer_b200.loss import shard_layout
+
+    b, W, D = 24, 3, 256
+    xs = [(rnd((b * W, D), 10 + 2 * t), rnd((b * W, D), 11 + 2 * t)) for t in range(2)]
+    refs = []
+    for x0, x1 in xs:
+        r0, r1 = x0.clone().requires_grad_(True), x1.clone().requires_grad_(True)
+        l = ntxent_ref(r0, r1, 0.1)
+        l.backward()
+        refs.append((l.item(), r0.grad, r1.grad))
+    n_r, n = 2 * b, 4 * b
+    packs = []
+    for r in range(W):
+        sl = slice(r * b, (r + 1) * b)
+        xp = torch.cat([xs[0][0][sl], xs[0][1][sl], xs[1][0][sl], xs[1][1][sl]], 0).contiguous()
+        packs.append(ops.l2norm_rows(xp))
+    zc = torch.cat([z for z, _ in packs], 0).contiguous()           # what all_gather_into_tensor produces
+    lse_all = torch.empty(W * n, device="cuda")
+    keep = []
+    for r in range(W):
+        z, norm = packs[r]
+        off, half = shard_layout(r, W, b)
+        for t in range(2):
+            loss = torch.zeros(1, device="cuda")
+            lse, S = ops.ntxent_fwd(z[t * n_r:(t + 1) * n_r], zc, b, off, half, 0.1, loss, n_c=W * n_r, colmap=(n_r, n, t * n_r),
+                                    lse_out=lse_all[r * n + t * n_r:r * n + (t + 1) * n_r])
+            keep.append((r, t, loss, S))
+    for t in range(2):
+        mean = torch.stack([l for r, tt, l, S in keep if tt == t]).mean().item()
+        assert abs(mean - refs[t][0]) < 1e-4 * max(1.0, abs(refs[t][0]))
+    for r, t, loss, S in keep:
+        z, norm = packs[r]
+        off, half = shard_layout(r, W, b)
+        dx = ops.ntxent_bwd(z[t * n_r:(t + 1) * n_r], norm[t * n_r:(t + 1) * n_r], zc, lse_all, S, b, off, half, 0.1,
+                            1.0 / (2 * b * W), n_c=W * n_r, colmap=(n_r, n, t * n_r))
+        close(dx[:b], refs[t][1][r * b:(r + 1) * b], tol=1e-3)
+        close(dx[b:], refs[t][2][r * b:(r + 1) * b], tol=1e-3)
+
+
 def test_adamw_matches_torch():
     from vipformer_b200 import ops
 

@@ -15,9 +15,11 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
 
-def oracle_run(cfg, dtype=torch.float32):
+def oracle_run(cfg, dtype=torch.float32, pins=None, drop=None, start=None):
     """Shared with the GPU tests: product-mirror init (identical to the reference's, asserted by make_golden_model.py)
-    -> perturbed state_dicts -> oracle forward/loss/backward."""
+    -> perturbed state_dicts -> oracle forward/loss/backward.
+    pins: discrete choices to impose (oracle.model_ref.choices); drop: kwargs of oracle.model_ref.dropout."""
+    import contextlib
     pc, im = _synth.build_models(cfg)
     sd_pc = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(pc.state_dict(), cfg["seed"] + 10).items()}
     sd_im = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(im.state_dict(), cfg["seed"] + 11).items()}
@@ -31,13 +33,15 @@ def oracle_run(cfg, dtype=torch.float32):
         for k in list(sd.keys()):
             if ".cross_attn_n." in k:
                 sd[k.replace(".cross_attn_n.", ".cross_attn_1.")] = sd[k]
-    pts, start, imgs = _synth.model_inputs(cfg)
+    pts, start0, imgs = _synth.model_inputs(cfg)
+    start = start0 if start is None else np.asarray(start)
     run_pc, run_im = {}, {}
-    pc_feats, pc_back = M.pc_forward(sd_pc, pts.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, run_pc)
-    im_feats, im_back = M.img_forward(sd_im, imgs.to(dtype), cfg["patch"], cfg["H"], cfg["n_sa"], True, run_im)
-    total, imid, cmid = M.pretrain_loss(pc_feats, im_feats)
-    total.backward()
-    return dict(sd_pc=sd_pc, sd_im=sd_im, pnames=pnames, inames=inames, pc_feats=pc_feats.detach(), pc_back=pc_back.detach(),
+    with M.choices(pins) as ch, (M.dropout(**drop) if drop else contextlib.nullcontext()):
+        pc_feats, pc_back = M.pc_forward(sd_pc, pts.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, run_pc)
+        im_feats, im_back = M.img_forward(sd_im, imgs.to(dtype), cfg["patch"], cfg["H"], cfg["n_sa"], True, run_im)
+        total, imid, cmid = M.pretrain_loss(pc_feats, im_feats)
+        total.backward()
+    return dict(rec=ch.rec, sd_pc=sd_pc, sd_im=sd_im, pnames=pnames, inames=inames, pc_feats=pc_feats.detach(), pc_back=pc_back.detach(),
                 im_feats=im_feats.detach(), im_back=im_back.detach(), loss=(total.item(), imid.item(), cmid.item()),
                 run_pc=run_pc, run_im=run_im, inputs=(pts, start, imgs))
 

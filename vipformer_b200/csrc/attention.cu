@@ -111,9 +111,9 @@ __device__ __forceinline__ void pack_p(uint32_t (&p)[4][4], const float (&s)[8][
   }
 }
 
-// Attention-probability dropout (partseg.py:81).  One 32-bit hash covers a 2x2 block of (query, key) positions, 8 bits
-// each: whichever way a thread's accumulator elements are paired (adjacent keys in the forward / dQ kernels, adjacent
-// queries in the dK/dV kernel) two elements share one hash.  Effective p = round(256 p) / 256 (0.1 -> 26/256).
+// Attention-probability dropout (partseg.py:81).  One 32-bit hash covers 4 ADJACENT KEYS of one query row, 8 bits each
+// (layout shared with attention_tc.cu, where a thread owns a row segment; restated in oracle/rng.py attention_keep).
+// Effective p = round(256 p) / 256 (0.1 -> 26/256 = 0.1016).
 struct DropCfg {
   uint32_t thr, key;   // thr: 8-bit threshold (0 = dropout off)
   float scale;
@@ -125,13 +125,13 @@ __device__ __forceinline__ DropCfg make_drop(float p, const unsigned long long *
   d.scale = d.thr ? 256.f / (256.f - (float)d.thr) : 1.f;
   return d;
 }
-// hash of the 2x2 block containing (i, j); element (i, j) uses byte ((i & 1) << 1) | (j & 1)
+// hash of the 4-key group containing (i, j); element (i, j) uses byte j & 3
 __device__ __forceinline__ uint32_t block_hash(const DropCfg &dc, int bh, int i, int j, int Lq, int Lk) {
-  const uint32_t idx = ((uint32_t)bh * (uint32_t)((Lq + 1) >> 1) + (uint32_t)(i >> 1)) * (uint32_t)((Lk + 1) >> 1) + (uint32_t)(j >> 1);
+  const uint32_t idx = ((uint32_t)bh * (uint32_t)Lq + (uint32_t)i) * (uint32_t)((Lk + 3) >> 2) + (uint32_t)(j >> 2);
   return rng::mix32(idx * 0x9e3779b1u ^ dc.key);
 }
 __device__ __forceinline__ bool keep_from(uint32_t hash, int i, int j, uint32_t thr) {
-  return ((hash >> ((((i & 1) << 1) | (j & 1)) * 8)) & 0xffu) >= thr;
+  return ((hash >> ((j & 3) * 8)) & 0xffu) >= thr;
 }
 
 // ------------------------------------------------------------------ forward
@@ -344,12 +344,10 @@ attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict_
     mma_a_tileT(dp, va, tdO, lane);   // dP^T[key][q] = V dO^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-      const int qe = nb * 8 + (lane & 3) * 2;   // even local query: (qe, qe+1) share a hash
+      const int qe = nb * 8 + (lane & 3) * 2;   // even local query
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const int j = jrow + h2 * 8;
-        uint32_t hsh = 0;
-        if (dc.thr) hsh = block_hash(dc, bh, q0 + qe, j, Lq, Lk);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           const int e = h2 * 2 + w, ql = qe + w;
@@ -357,7 +355,7 @@ attn_bwd_dkv_kernel(const bf16 *__restrict__ Q, int ldq, const bf16 *__restrict_
           float dpe = dp[nb][e];
           float pd = p;
           if (dc.thr) {
-            const bool keep = keep_from(hsh, q0 + ql, j, dc.thr);
+            const bool keep = keep_from(block_hash(dc, bh, q0 + ql, j, Lq, Lk), q0 + ql, j, dc.thr);
             pd = keep ? p * dc.scale : 0.f;
             dpe = keep ? dpe * dc.scale : 0.f;
           }

@@ -7,6 +7,8 @@
 //   loss = mean_i [ logsumexp_{j != i} s_ij - s_{i,pos(i)} ],  s_ij = z_i . z_j / T
 // Global-negative extension: rows are this rank's 2b embeddings, columns are the
 // all-gathered 2bW embeddings; local row i sits at column self(i), its positive at pos(i).
+// Column j of the logits lives at physical row  (j / blk) * ld + base + j % blk  of the gathered buffer (ColMap): one
+// NCCL all-gather of every rank's PACKED [imid rows | cmid rows] block then serves both loss terms without a re-layout.
 // AdamW follows torch.optim.AdamW defaults (pretrain.py:121-124).
 #include "common.cuh"
 
@@ -30,6 +32,9 @@ l2norm_rows_kernel(const float *__restrict__ x, float *__restrict__ z, float *__
   if (lane == 0) norm[row] = nr;
 }
 
+struct ColMap { int blk, ld, base; };
+__device__ __forceinline__ size_t phys(const ColMap &c, int j) { return (size_t)(j / c.blk) * c.ld + c.base + (j % c.blk); }
+
 __device__ __forceinline__ void self_pos(int i, int b_local, int col_offset, int half, int &self, int &pos) {
   if (i < b_local) { self = col_offset + i; pos = half + col_offset + i; }
   else { self = half + col_offset + (i - b_local); pos = col_offset + (i - b_local); }
@@ -41,7 +46,7 @@ __device__ __forceinline__ void self_pos(int i, int b_local, int col_offset, int
 constexpr int kSgTile = 64, kSgK = 64;   // K slab of 64: 4x fewer load -> sync -> FMA -> sync rounds than 16 (the kernel is latency bound: 32-64 CTAs)
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K,
-             float alpha, int b_nt) {
+             float alpha, int b_nt, ColMap cm) {   // cm maps the logits-column index (n if b_nt, else k) to a row of B
   __shared__ float sA[kSgK][kSgTile + 4], sB[kSgK][kSgTile + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * kSgTile, n0 = blockIdx.x * kSgTile;
@@ -57,14 +62,14 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
       sA[kk][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
       if (b_nt) {
         const int n = n0 + r;
-        sB[kk][r] = (n < N && k < K) ? B[(size_t)n * K + k] : 0.f;
+        sB[kk][r] = (n < N && k < K) ? B[phys(cm, n) * K + k] : 0.f;
       }
     }
     if (!b_nt) {
       for (int t = threadIdx.x; t < kSgTile * kSgK; t += 256) {
         const int kk = t / kSgTile, c = t % kSgTile;   // B tile: rows k, contiguous in n
         const int k = k0 + kk, n = n0 + c;
-        sB[kk][c] = (n < N && k < K) ? B[(size_t)k * N + n] : 0.f;
+        sB[kk][c] = (n < N && k < K) ? B[phys(cm, k) * N + n] : 0.f;
       }
     }
     __syncthreads();
@@ -118,7 +123,7 @@ ntxent_rowlse_kernel(const float *__restrict__ S, int n_r, int n_c, int b_local,
 // in place: S[k,j] <- w_kj = [j != self(k)] (exp(s - lse_k) + exp(s - lse_all[j])) - 2 [j == pos(k)]
 __global__ void __launch_bounds__(256)
 ntxent_weights_kernel(float *__restrict__ S, const float *__restrict__ lse_all, int n_r, int n_c, int b_local,
-                      int col_offset, int half) {
+                      int col_offset, int half, ColMap cm) {
   const size_t total = (size_t)n_r * n_c;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
     const int k = (int)(e / n_c), j = (int)(e % n_c);
@@ -126,7 +131,7 @@ ntxent_weights_kernel(float *__restrict__ S, const float *__restrict__ lse_all, 
     self_pos(k, b_local, col_offset, half, self, pos);
     const float s = S[e];
     float w = 0.f;
-    if (j != self) w = __expf(s - lse_all[self]) + __expf(s - lse_all[j]);
+    if (j != self) w = __expf(s - lse_all[phys(cm, self)]) + __expf(s - lse_all[phys(cm, j)]);
     if (j == pos) w -= 2.f;
     S[e] = w;
   }
@@ -188,29 +193,40 @@ int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *s
   return check_launch("l2norm_rows_kernel");
 }
 
+static int check_cols(const char *what, int n_r, int n_c, int b_local, int col_offset, int half, float temperature,
+                      int zc_blk, int zc_ld) {
+  VPF_REQUIRE(n_r == 2 * b_local && half >= b_local && col_offset >= 0 && col_offset + half + b_local <= n_c && temperature > 0.f,
+              "%s: inconsistent sizes (n_r=%d n_c=%d b=%d col_offset=%d half=%d)", what, n_r, n_c, b_local, col_offset, half);
+  VPF_REQUIRE(zc_blk >= 1 && zc_ld >= zc_blk, "%s: bad column map (blk=%d ld=%d)", what, zc_blk, zc_ld);
+  return VPF_OK;
+}
+
 int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local, int col_offset, int half,
-                   float temperature, float *S_ws, float *lse_out, float *loss_out, void *stream) {
+                   int zc_blk, int zc_ld, int zc_base, float temperature, float *S_ws, float *lse_out, float *loss_out,
+                   void *stream) {
   VPF_REQUIRE(zr && zc && S_ws && lse_out && loss_out, "ntxent_fwd: null pointer");
-  VPF_REQUIRE(n_r == 2 * b_local && n_c == 2 * half && col_offset >= 0 && col_offset + b_local <= half && temperature > 0.f, "ntxent_fwd: inconsistent sizes");
+  VPF_TRY(check_cols("ntxent_fwd", n_r, n_c, b_local, col_offset, half, temperature, zc_blk, zc_ld));
   if (n_r == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  sgemm_kernel<<<dim3(ceil_div(n_c, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(zr, zc, S_ws, n_r, n_c, D, 1.f / temperature, 1);
+  const ColMap cm{zc_blk, zc_ld, zc_base};
+  sgemm_kernel<<<dim3(ceil_div(n_c, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(zr, zc, S_ws, n_r, n_c, D, 1.f / temperature, 1, cm);
   VPF_TRY(check_launch("sgemm_kernel"));
   ntxent_rowlse_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(S_ws, n_r, n_c, b_local, col_offset, half, lse_out, loss_out);
   return check_launch("ntxent_rowlse_kernel");
 }
 
 int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all, int n_c, int D,
-                   int b_local, int col_offset, int half, float temperature, float gscale, const float *upstream,
-                   float *S_ws, float *G_ws, float *dx, void *stream) {
+                   int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base, float temperature,
+                   float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream) {
   VPF_REQUIRE(zr && norm && zc && lse_all && S_ws && G_ws && dx, "ntxent_bwd: null pointer");
-  VPF_REQUIRE(n_r == 2 * b_local && n_c == 2 * half && col_offset >= 0 && col_offset + b_local <= half && temperature > 0.f, "ntxent_bwd: inconsistent sizes");
+  VPF_TRY(check_cols("ntxent_bwd", n_r, n_c, b_local, col_offset, half, temperature, zc_blk, zc_ld));
   if (n_r == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)n_r * n_c;
-  ntxent_weights_kernel<<<(int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)), 256, 0, st>>>(S_ws, lse_all, n_r, n_c, b_local, col_offset, half);
+  const ColMap cm{zc_blk, zc_ld, zc_base};
+  ntxent_weights_kernel<<<(int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)), 256, 0, st>>>(S_ws, lse_all, n_r, n_c, b_local, col_offset, half, cm);
   VPF_TRY(check_launch("ntxent_weights_kernel"));
-  sgemm_kernel<<<dim3(ceil_div(D, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(S_ws, zc, G_ws, n_r, D, n_c, 1.f, 0);
+  sgemm_kernel<<<dim3(ceil_div(D, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(S_ws, zc, G_ws, n_r, D, n_c, 1.f, 0, cm);
   VPF_TRY(check_launch("sgemm_kernel"));
   l2norm_bwd_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(G_ws, zr, norm, gscale / temperature, upstream, dx, n_r, D);
   return check_launch("l2norm_bwd_kernel");

@@ -2,9 +2,10 @@
 plus the fused loss composition of pretrain.py:189-207.
 
 Kernels (csrc/loss_optim.cu): row normalisation, fp32 similarity GEMM into a small logits scratch ([2b, 2bW]; 1 MB
-at b = 256), masked row log-sum-exp + reduction; backward = weights in place, fp32 GEMM, normalisation backward.  With gather_distributed=True the columns are the
-all-gathered embeddings of every rank (NCCL all-gather of the L2-normalised rows; the backward needs only an
-all-gather of the per-row log-sum-exp vector) so negatives span the global batch.
+at b = 256), masked row log-sum-exp + reduction; backward = weights in place, fp32 GEMM, normalisation backward.  With
+gather_distributed=True the columns are the all-gathered embeddings of every rank so negatives span the global batch:
+per step ONE NCCL all-gather of the packed L2-normalised rows of both loss terms and ONE of their per-row log-sum-exps
+(SURVEY.md 8e), both issued in the forward pass -- the backward is collective-free.
 """
 import torch
 import torch.nn as nn
@@ -23,9 +24,10 @@ def _dist():
 
 
 def shard_layout(rank, world, b):
-    """Column layout of the all-gathered embeddings: cat(all ranks' out0 blocks, all ranks' out1 blocks).
-    Returns (col_offset, half): local row i < b sits at column col_offset + i, row b + i at half + col_offset + i."""
-    return rank * b, world * b
+    """Column layout of the all-gathered embeddings (rank-major): rank r contributes the 2b columns
+    [2rb, 2rb + b) = its out0 rows and [2rb + b, 2rb + 2b) = its out1 rows.
+    Returns (col_offset, half): local row i < b sits at column col_offset + i, row b + i at col_offset + half + i."""
+    return 2 * rank * b, b
 
 
 def self_pos_columns(i, b, col_offset, half):
@@ -35,51 +37,64 @@ def self_pos_columns(i, b, col_offset, half):
     return half + col_offset + (i - b), col_offset + (i - b)
 
 
-def _stack2(a, b):
-    """[a; b] as one contiguous fp32 [2b, D] buffer (copy kernels, no ATen cat)."""
-    n, D = a.shape
-    x = torch.empty((2 * n, D), dtype=F32, device=a.device)
-    ops.add_scale(a.float().contiguous(), None, 1.0, out=x[:n])
-    ops.add_scale(b.float().contiguous(), None, 1.0, out=x[n:])
-    return x
+def _copy_rows(src, dst):
+    ops.add_scale(src.float().contiguous(), None, 1.0, out=dst)
 
 
-class _NTXentCore:
-    """forward/backward on a stacked [2b, D] input; shared by the autograd functions below."""
+class _NTXentPack:
+    """forward/backward of `nseg` NT-Xent terms that share ONE all-gather of the normalised embeddings and ONE of the
+    per-row log-sum-exps (both issued in the FORWARD pass, on the caller's thread and stream: nothing collective runs
+    inside autograd's backward, which is what lets the whole step be captured in a CUDA graph with world_size > 1).
+
+    x_pack [nseg * 2b, D]: segment s holds the stacked [out0; out1] rows of term s.  Every rank gathers the packed
+    block, so logits column j of term s lives at row (j // 2b) * (nseg * 2b) + s * 2b + j % 2b of the gathered buffer
+    (the ColMap of loss_optim.cu) -- no re-layout copy."""
 
     @staticmethod
-    def fwd(x, temperature, gather):
-        n, D = x.shape
-        b = n // 2
-        z, norm = ops.l2norm_rows(x)
+    def fwd(x_pack, nseg, temperature, gather):
+        n, D = x_pack.shape
+        n_r = n // nseg
+        b = n_r // 2
+        dev = x_pack.device
+        z, norm = ops.l2norm_rows(x_pack)
         dist = _dist() if gather else None
+        W, r = (dist.get_world_size(), dist.get_rank()) if dist is not None else (1, 0)
         if dist is not None:
-            W, r = dist.get_world_size(), dist.get_rank()
-            zc = torch.empty((2 * W * b, D), dtype=F32, device=x.device)
-            dist.all_gather_into_tensor(zc[:W * b], z[:b].contiguous())
-            dist.all_gather_into_tensor(zc[W * b:], z[b:].contiguous())
-            col_offset, half = shard_layout(r, W, b)
+            zc = torch.empty((W * n, D), dtype=F32, device=dev)
+            dist.all_gather_into_tensor(zc, z)
         else:
-            zc, col_offset, half = z, 0, b
-        loss = ops.zeros_(torch.empty(1, dtype=F32, device=x.device))
-        lse, S = ops.ntxent_fwd(z, zc, b, col_offset, half, temperature, loss)
-        return loss, [z, norm, zc, lse, b, col_offset, half, temperature, dist, S]
+            zc = z
+        col_offset, half = shard_layout(r, W, b)
+        n_c = W * n_r
+        losses = ops.zeros_(torch.empty(nseg, dtype=F32, device=dev))
+        lse = torch.empty(n, dtype=F32, device=dev)
+        S = []
+        for s in range(nseg):
+            cm = (n_r, n, s * n_r)
+            _, Ss = ops.ntxent_fwd(z[s * n_r:(s + 1) * n_r], zc, b, col_offset, half, temperature, losses[s:s + 1],
+                                   n_c=n_c, colmap=cm, lse_out=lse[s * n_r:(s + 1) * n_r])
+            S.append(Ss)
+        if dist is not None:
+            lse_all = torch.empty(W * n, dtype=F32, device=dev)
+            dist.all_gather_into_tensor(lse_all, lse)
+        else:
+            lse_all = lse
+        return losses, dict(z=z, norm=norm, zc=zc, lse_all=lse_all, S=S, b=b, n_r=n_r, n=n, n_c=n_c, col_offset=col_offset,
+                            half=half, T=temperature)
 
     @staticmethod
-    def bwd(saved, gscale, upstream=None):
-        z, norm, zc, lse, b, col_offset, half, temperature, dist, S = saved
+    def bwd(sv, seg, gscale, upstream=None):
+        """-> gradient [2b, D] w.r.t. segment `seg`'s stacked rows."""
+        S = sv["S"][seg]
         if S is None:
             raise RuntimeError("NT-Xent backward ran twice on one forward: its logits scratch is overwritten in place by "
                                "the first backward (retain_graph=True is not supported by this fused loss)")
-        if dist is not None:
-            lse_all = torch.empty(2 * half, dtype=F32, device=z.device)
-            dist.all_gather_into_tensor(lse_all[:half], lse[:b].contiguous())
-            dist.all_gather_into_tensor(lse_all[half:], lse[b:].contiguous())
-        else:
-            lse_all = lse
-        saved[-1] = None
+        sv["S"][seg] = None
+        n_r, b = sv["n_r"], sv["b"]
+        sl = slice(seg * n_r, (seg + 1) * n_r)
         # DDP averages parameter gradients over ranks, so the per-rank seed stays 1/(2b) for any world size
-        return ops.ntxent_bwd(z, norm, zc, lse_all, S, b, col_offset, half, temperature, gscale / (2 * b), upstream)
+        return ops.ntxent_bwd(sv["z"][sl], sv["norm"][sl], sv["zc"], sv["lse_all"], S, b, sv["col_offset"], sv["half"],
+                              sv["T"], gscale / (2 * b), upstream, n_c=sv["n_c"], colmap=(n_r, sv["n"], seg * n_r))
 
 
 class _NTXentFn(torch.autograd.Function):
@@ -88,15 +103,19 @@ class _NTXentFn(torch.autograd.Function):
         _lib.require_cuda(out0, out1)
         if out0.shape != out1.shape or out0.dim() != 2:
             raise ValueError("NTXentLoss expects two [batch, dim] tensors of equal shape")
-        loss, saved = _NTXentCore.fwd(_stack2(out0, out1), temperature, gather)
+        b, D = out0.shape
+        x = torch.empty((2 * b, D), dtype=F32, device=out0.device)
+        _copy_rows(out0, x[:b])
+        _copy_rows(out1, x[b:])
+        loss, saved = _NTXentPack.fwd(x, 1, temperature, gather)
         ctx.saved = saved
         return loss.view(())
 
     @staticmethod
     def backward(ctx, dloss):
         up = dloss.float().reshape(1).contiguous()
-        dx = _NTXentCore.bwd(ctx.saved, 1.0, up)
-        b = ctx.saved[4]
+        dx = _NTXentPack.bwd(ctx.saved, 0, 1.0, up)
+        b = ctx.saved["b"]
         return dx[:b], dx[b:], None, None
 
 
@@ -123,23 +142,26 @@ class _PretrainLossFn(torch.autograd.Function):
     def forward(ctx, pc_feats, img_feats, temperature, cmid_weight, gather):
         _lib.require_cuda(pc_feats, img_feats)
         pc = pc_feats.float().contiguous()
-        b = pc.shape[0] // 2
-        l_imid, s_imid = _NTXentCore.fwd(pc, temperature, gather)          # rows already stacked as [t1; t2]
-        avg = ops.add_scale(pc[:b], pc[b:], 0.5)
-        l_cmid, s_cmid = _NTXentCore.fwd(_stack2(avg, img_feats), temperature, gather)
+        n_r, D = pc.shape
+        b = n_r // 2
+        # packed rows: [t1; t2 | (t1+t2)/2; img]  -> one normalisation, one all-gather
+        x = torch.empty((2 * n_r, D), dtype=F32, device=pc.device)
+        _copy_rows(pc, x[:n_r])
+        ops.add_scale(pc[:b], pc[b:], 0.5, out=x[n_r:n_r + b])
+        _copy_rows(img_feats, x[n_r + b:])
+        l, saved = _NTXentPack.fwd(x, 2, temperature, gather)
         total = torch.empty(3, dtype=F32, device=pc.device)
-        ops.add_scale(l_imid, None, 1.0, out=total[1:2])
-        ops.add_scale(l_cmid, None, 1.0, out=total[2:3])
-        ops.add_scale(l_imid, ops.add_scale(l_cmid, None, float(cmid_weight)), 1.0, out=total[0:1])
-        ctx.saved = (s_imid, s_cmid, b, float(cmid_weight))
+        ops.add_scale(l, None, 1.0, out=total[1:3])
+        ops.add_scale(l[0:1], ops.add_scale(l[1:2], None, float(cmid_weight)), 1.0, out=total[0:1])
+        ctx.saved = (saved, b, float(cmid_weight))
         return total
 
     @staticmethod
     def backward(ctx, dtotal):
-        s_imid, s_cmid, b, w = ctx.saved
+        saved, b, w = ctx.saved
         up = dtotal.float().contiguous()[0:1]      # gradients flow through total[0] only (entries 1,2 are for logging)
-        d_imid = _NTXentCore.bwd(s_imid, 1.0, up)                 # [2b, D] w.r.t. [t1; t2]
-        d_cmid = _NTXentCore.bwd(s_cmid, w, up)                   # [2b, D] w.r.t. [(t1+t2)/2; img]
+        d_imid = _NTXentPack.bwd(saved, 0, 1.0, up)               # [2b, D] w.r.t. [t1; t2]
+        d_cmid = _NTXentPack.bwd(saved, 1, w, up)                 # [2b, D] w.r.t. [(t1+t2)/2; img]
         half = ops.add_scale(d_cmid[:b], None, 0.5)
         dpc = torch.empty_like(d_imid)
         ops.add_scale(d_imid[:b], half, 1.0, out=dpc[:b])

@@ -50,6 +50,7 @@ class _AdapterFn(torch.autograd.Function):
         W = NS(w1=m[0].weight, b1=m[0].bias, ln_w=m[1].weight, ln_b=m[1].bias, w2=params.wb(m[3].weight), b2=m[3].bias)
         save = any(ctx.needs_input_grad)
         e, c = Fn.adapter_fwd(pts, W, save)
+        rt.tap("adapter", c)
         if save:
             ctx.c, ctx.mod, ctx.arena, ctx.W = c, mod, arena, W
         return e.view(pts.shape[0], pts.shape[1], -1)

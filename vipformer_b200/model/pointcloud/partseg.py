@@ -431,6 +431,7 @@ class _PoolHeadFn(torch.autograd.Function):
         bn = NS(rm1=mod[0].running_mean, rv1=mod[0].running_var, rm2=mod[3].running_mean, rv2=mod[3].running_var)
         save = any(ctx.needs_input_grad)
         feats, pooled, c = Fn.pool_head_fwd(_as_f32_2d(x, D), W, bn, B, L, D, mod.training, save)
+        _rt.tap("head", c)
         if mod.training:
             _bump(mod[0]); _bump(mod[3])
         if save:

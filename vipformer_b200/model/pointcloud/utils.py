@@ -188,6 +188,7 @@ class _Group2EmbFn(torch.autograd.Function):
         W = mod._weights()
         save = any(ctx.needs_input_grad)
         tok, c = _Fn.group2emb_fwd(nb, W, bn, cfg, mod.training, save)
+        _rt.tap("g2e", c)
         if mod.training:
             _rt.bump(f[1]); _rt.bump(s[1])
         if save:

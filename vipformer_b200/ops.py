@@ -285,30 +285,37 @@ def patchify(img, P, nchw=False):
 
 
 # ----------------------------------------------------------------------------- loss / optimiser
-def l2norm_rows(x):
+def l2norm_rows(x, z=None, norm=None):
     n, D = x.shape
-    z = torch.empty_like(x)
-    norm = torch.empty(n, dtype=F32, device=x.device)
+    z = torch.empty_like(x) if z is None else z
+    norm = torch.empty(n, dtype=F32, device=x.device) if norm is None else norm
     _lib.call("vpf_l2norm_rows", _p(x), _p(z), _p(norm), _i(n), _i(D), _s())
     return z, norm
 
 
-def ntxent_fwd(zr, zc, b_local, col_offset, half, temperature, loss_out):
-    """-> (lse [n_r], logits scratch S [n_r, n_c] to hand to ntxent_bwd)."""
+def ntxent_fwd(zr, zc, b_local, col_offset, half, temperature, loss_out, n_c=None, colmap=None, lse_out=None):
+    """-> (lse [n_r], logits scratch S [n_r, n_c] to hand to ntxent_bwd).  colmap = (blk, ld, base) maps logits column j
+    to row (j // blk) * ld + base + j % blk of zc (default: zc is a plain [n_c, D] buffer)."""
     n_r, D = zr.shape
-    lse = torch.empty(n_r, dtype=F32, device=zr.device)
-    S = torch.empty((n_r, zc.shape[0]), dtype=F32, device=zr.device)
-    _lib.call("vpf_ntxent_fwd", _p(zr), _i(n_r), _p(zc), _i(zc.shape[0]), _i(D), _i(b_local), _i(col_offset), _i(half),
-              _f(temperature), _p(S), _p(lse), _p(loss_out), _s())
+    n_c = zc.shape[0] if n_c is None else n_c
+    blk, ld, base = (n_c, n_c, 0) if colmap is None else colmap
+    lse = torch.empty(n_r, dtype=F32, device=zr.device) if lse_out is None else lse_out
+    S = torch.empty((n_r, n_c), dtype=F32, device=zr.device)
+    _lib.call("vpf_ntxent_fwd", _p(zr), _i(n_r), _p(zc), _i(n_c), _i(D), _i(b_local), _i(col_offset), _i(half),
+              _i(blk), _i(ld), _i(base), _f(temperature), _p(S), _p(lse), _p(loss_out), _s())
     return lse, S
 
 
-def ntxent_bwd(zr, norm, zc, lse_all, S, b_local, col_offset, half, temperature, gscale, upstream=None):
+def ntxent_bwd(zr, norm, zc, lse_all, S, b_local, col_offset, half, temperature, gscale, upstream=None, n_c=None,
+               colmap=None):
     n_r, D = zr.shape
+    n_c = zc.shape[0] if n_c is None else n_c
+    blk, ld, base = (n_c, n_c, 0) if colmap is None else colmap
     dx = torch.empty((n_r, D), dtype=F32, device=zr.device)
     G = torch.empty((n_r, D), dtype=F32, device=zr.device)
-    _lib.call("vpf_ntxent_bwd", _p(zr), _p(norm), _i(n_r), _p(zc), _p(lse_all), _i(zc.shape[0]), _i(D), _i(b_local),
-              _i(col_offset), _i(half), _f(temperature), _f(gscale), _p(upstream), _p(S), _p(G), _p(dx), _s())
+    _lib.call("vpf_ntxent_bwd", _p(zr), _p(norm), _i(n_r), _p(zc), _p(lse_all), _i(n_c), _i(D), _i(b_local),
+              _i(col_offset), _i(half), _i(blk), _i(ld), _i(base), _f(temperature), _f(gscale), _p(upstream), _p(S), _p(G),
+              _p(dx), _s())
     return dx
 
 
