@@ -15,7 +15,16 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
 
-def oracle_run(cfg, dtype=torch.float32, pins=None, drop=None, start=None):
+def linear_upstream(cfg):
+    """Fixed pseudo-random upstream gradients for (pc_feats, pc_backbone, img_feats, img_backbone): the 'loss' is the
+    linear functional sum <output, G>, which takes NT-Xent's T = 0.1 noise amplification out of a gradient comparison."""
+    g = torch.Generator().manual_seed(cfg["seed"] + 99)
+    b, D = cfg["b"], cfg["D"]
+    return (torch.randn((2 * b, D), generator=g), 0.1 * torch.randn((2 * b, 2 * D), generator=g),
+            torch.randn((b, D), generator=g), 0.1 * torch.randn((b, 2 * D), generator=g))
+
+
+def oracle_run(cfg, dtype=torch.float32, pins=None, drop=None, start=None, linear=False):
     """Shared with the GPU tests: product-mirror init (identical to the reference's, asserted by make_golden_model.py)
     -> perturbed state_dicts -> oracle forward/loss/backward.
     pins: discrete choices to impose (oracle.model_ref.choices); drop: kwargs of oracle.model_ref.dropout."""
@@ -40,7 +49,11 @@ def oracle_run(cfg, dtype=torch.float32, pins=None, drop=None, start=None):
         pc_feats, pc_back = M.pc_forward(sd_pc, pts.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, run_pc)
         im_feats, im_back = M.img_forward(sd_im, imgs.to(dtype), cfg["patch"], cfg["H"], cfg["n_sa"], True, run_im)
         total, imid, cmid = M.pretrain_loss(pc_feats, im_feats)
-        total.backward()
+        if linear:
+            G = linear_upstream(cfg)
+            sum((t * g.to(dtype)).sum() for t, g in zip((pc_feats, pc_back, im_feats, im_back), G)).backward()
+        else:
+            total.backward()
     return dict(rec=ch.rec, sd_pc=sd_pc, sd_im=sd_im, pnames=pnames, inames=inames, pc_feats=pc_feats.detach(), pc_back=pc_back.detach(),
                 im_feats=im_feats.detach(), im_back=im_back.detach(), loss=(total.item(), imid.item(), cmid.item()),
                 run_pc=run_pc, run_im=run_im, inputs=(pts, start, imgs))

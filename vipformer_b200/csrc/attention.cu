@@ -9,6 +9,7 @@
 //
 // Layout: Q rows are token rows of a [B*Lq, ldq] bf16 array, head h at columns [h*64, h*64+64);
 // K/V likewise in [B*Lk, ldkv]; O in [B*Lq, ldo].  LSE is fp32 [B*H, Lq] in log2 units.
+#include <stdlib.h>
 #include "common.cuh"
 #include "rng.cuh"
 
@@ -658,6 +659,22 @@ template <typename Kern> static int set_smem(Kern k, int bytes) {
   return VPF_OK;
 }
 
+// tcgen05 / TMEM path (attention_tc.cu): every attention with Lq <= 128 query tokens (the point-cloud branch)
+namespace atc {
+int attention_tc_fwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, void *O, int ldo, float *LSE, int B,
+                     int H, int Lq, int Lk, float scale, float drop_p, const unsigned long long *seed_ptr,
+                     unsigned int op_id, cudaStream_t st);
+int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, const void *O, int ldo, const void *dO,
+                     int lddo, const float *LSE, void *dQ, int lddq, void *dK, void *dV, int lddkv, int B, int H, int Lq,
+                     int Lk, float scale, float drop_p, const unsigned long long *seed_ptr, unsigned int op_id,
+                     cudaStream_t st);
+}  // namespace atc
+static bool use_tc(int Lq) {
+  static const int off = [] { const char *v = getenv("VPF_ATTN_TC"); return (v && v[0] == '0') ? 1 : 0; }();   // experiments: VPF_ATTN_TC=0
+  return !off && Lq <= 128;
+}
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace vpf
 
 using namespace vpf;
@@ -672,6 +689,8 @@ int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE(Lq >= 1 && Lk >= 1 && H >= 1 && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0, "attention_fwd: bad shape/stride");
   VPF_REQUIRE((long long)B * H <= 65535 * 1LL * 65535, "attention_fwd: too many heads");
   if (B == 0) return VPF_OK;
+  if (use_tc(Lq) && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O))
+    return atc::attention_tc_fwd(Q, ldq, K, V, ldkv, O, ldo, LSE, B, H, Lq, Lk, scale, drop_p, seed_ptr, op_id, (cudaStream_t)stream);
   if (Lq > 128 && Lq <= 160) {   // image branch (144 tokens): all queries in one 10-warp CTA, K/V streamed once
     const int smem = (160 + 4 * 64) * HD * 2;
     VPF_TRY(set_smem(attn_fwd_kernel<10>, smem));
@@ -700,6 +719,10 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE((ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddkv % 2) == 0, "attention_bwd: bad stride");
   if (B == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(Lq) && (lddq % 8) == 0 && (lddkv % 8) == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) &&
+      aligned16(dO) && aligned16(dQ) && aligned16(dK) && aligned16(dV))
+    return atc::attention_tc_bwd(Q, ldq, K, V, ldkv, O, ldo, dO, lddo, LSE, dQ, lddq, dK, dV, lddkv, B, H, Lq, Lk, scale, drop_p,
+                                 seed_ptr, op_id, st);
 #define FUSED_ARGS (const bf16 *)Q, ldq, (const bf16 *)K, (const bf16 *)V, ldkv, (const bf16 *)O, ldo, (const bf16 *)dO, lddo, LSE, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H, Lq, Lk, scale, drop_p, seed_ptr, op_id
   if (Lq <= 128) {
     const int smem = (4 * 128 + 4 * 64) * HD * 2;

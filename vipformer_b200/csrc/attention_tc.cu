@@ -1,0 +1,652 @@
+// attention_tc.cu -- the attention core of partseg.py:67-86 on the 5th-generation tensor cores:
+//   softmax(Q K^T * scale) -> dropout(p) -> . V   per (sample, head), head dim 64, Lq <= 128 query tokens
+// (the 96 / 128 latent tokens of every point-cloud layer: self-attention over 128 keys, cross-attention over
+// the 1024..2500 points of the cloud), forward and backward.  tcgen05.mma issued by one elected thread, operands
+// staged in shared memory by TMA (3-D maps [sample][token][channel]: out-of-range tokens are zero-filled), S / dP /
+// P.V / dQ / dK / dV accumulators in TMEM, softmax arithmetic thread-per-row straight from tcgen05.ld, P / dS handed
+// back to the tensor core through 128B-swizzled shared-memory tiles.  Logits never touch HBM.
+//
+// One shared-memory tile = [128 rows][64 bf16] (rows of 128 B, 16-byte chunks XOR-swizzled by row & 7 = the TMA
+// SWIZZLE_128B pattern), used through UMMA descriptors either K-major (rows = M/N index, the 64 columns = K) or
+// MN-major (rows = K index, the 64 columns = M/N), exactly the two forms gemm.cu uses:
+//   forward :  S  = Q K^T      A = Q  (K-major)        B = K  (K-major)      M 128, N 128, K 64
+//              O += P V        A = P  (K-major)        B = V  (MN-major)     M 128, N 64,  K 128
+//   backward:  S  = Q K^T, dP = dO V^T                  (as above)
+//              dV += P^T dO    A = P  (MN-major)       B = dO (MN-major)     M 128 keys, N 64, K 128 queries
+//              dK += dS^T Q    A = dS (MN-major)       B = Q  (MN-major)
+//              dQ += dS K      A = dS (K-major)        B = K  (MN-major)     M 128 queries, N 64, K 128 keys
+// so Q, K, V, dO are loaded once and P, dS written once per (query block, key block) pair.
+//
+// Dropout on the attention probabilities (partseg.py:81): keep(i, j) = byte (j & 3) of hash(seed, op, (bh, i, j >> 2))
+// >= round(256 p) -- one 32-bit hash serves 4 adjacent keys of a row; regenerated in the backward pass
+// (same function as attention.cu; restated in oracle/rng.py).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace vpf {
+namespace atc {
+
+typedef __nv_bfloat16 bf16;
+constexpr int HD = 64;
+constexpr int kTile = 128 * HD * 2;   // 16 KB
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- small PTX helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_s, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_s), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a [128][64] bf16 tile
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct Drop {
+  uint32_t thr, key;
+  float scale;
+};
+__device__ __forceinline__ Drop make_drop(float p, const unsigned long long *seed_ptr, uint32_t op_id) {
+  Drop d;
+  d.thr = p > 0.f ? (uint32_t)(p * 256.f + 0.5f) : 0u;
+  d.key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
+  d.scale = d.thr ? 256.f / (256.f - (float)d.thr) : 1.f;
+  return d;
+}
+// hash of the 4-key group g4 (= j >> 2) of row `rowbase` (= (bh * Lq + i) * ceil(Lk / 4))
+__device__ __forceinline__ uint32_t quad_hash(const Drop &dc, uint32_t rowbase, uint32_t g4) {
+  return rng::mix32((rowbase + g4) * 0x9e3779b1u ^ dc.key);
+}
+
+// UMMA issue helpers (one elected thread)
+__device__ __forceinline__ void mma_kmajor_kmajor(uint32_t tmem_d, uint32_t a_s, uint32_t b_s, int ksteps, uint32_t idesc, bool acc0) {
+  // A, B: K-major tiles, K advances 32 B per UMMA_K (16 bf16) inside the 128-byte swizzled row
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < ksteps)
+      ptx::umma_bf16(tmem_d, ptx::umma_smem_desc(a_s + k * 32, 16, 1024), ptx::umma_smem_desc(b_s + k * 32, 16, 1024), idesc,
+                     (acc0 || k > 0) ? 1u : 0u);
+  }
+}
+
+// =================================================================================================== forward
+// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax (thread = one query row x one 64-key half
+// of the 128-key block; O columns split the same way).  Two CTAs per SM (112.6 KB shared memory, 256 TMEM columns each).
+// Persistent over (sample, head) items; key blocks of 128 stream through a 2-stage K/V ring.
+constexpr int kFwdThreads = 320;
+constexpr int kFOffQ = 0, kFOffKV = kTile, kFOffP = kFOffKV + 4 * kTile, kFOffX = kFOffP + 2 * kTile, kFOffBar = kFOffX + 512;
+constexpr int kFwdSmem = kFOffBar + 128;
+static_assert(kFwdSmem <= 115712, "two forward CTAs per SM");
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, bf16 *__restrict__ O, int ldo, float *__restrict__ LSE,
+                   int H, int Lq, int Lk, int n_items, float scale, float drop_p,
+                   const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_s = ptx::smem_u32(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFOffBar);
+  uint64_t *q_full = bars + 0, *q_empty = bars + 1, *kv_full = bars + 2, *kv_empty = bars + 4, *s_full = bars + 6,
+           *s_empty = bars + 7, *p_full = bars + 8, *pv_full = bars + 9, *pv_empty = bars + 10;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+  float *xl = reinterpret_cast<float *>(smem + kFOffX);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (Lk + 127) >> 7;
+
+  if (threadIdx.x == 0 && (smem_s & 1023u)) __trap();   // the swizzled tiles need a 1024-byte aligned base
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
+      ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, 8); ptx::mbar_init(p_full, 8);
+      ptx::mbar_init(pv_full, 1); ptx::mbar_init(pv_empty, 8);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQ = smem_s + kFOffQ, sKV = smem_s + kFOffKV, sP = smem_s + kFOffP;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int n = 0, j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      const int b = it / H, h = it - b * H;
+      ptx::mbar_wait(q_empty, (j & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(q_full, kTile);
+        tma_load_3d(sQ, &tmQ, q_full, h * HD, 0, b);
+      }
+      __syncwarp();
+      for (int t = 0; t < nkb; ++t, ++n) {
+        const int st = n & 1;
+        ptx::mbar_wait(&kv_empty[st], ((n >> 1) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+          tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
+          tma_load_3d(sKV + st * 2 * kTile + kTile, &tmV, &kv_full[st], h * HD, t * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0), idesc_pv = ptx::umma_idesc_bf16(128, 64, 0, 1);
+    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_items * nkb;
+    auto issue_s = [&](int n) {
+      const int t = n % nkb, j = n / nkb, st = n & 1;
+      if (t == 0) ptx::mbar_wait(q_full, j & 1);
+      ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
+      ptx::mbar_wait(s_empty, (n & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        mma_kmajor_kmajor(tmem_base, sQ, sKV + st * 2 * kTile, 4, idesc_s, false);
+        ptx::umma_commit(s_full);
+        if (t == nkb - 1) ptx::umma_commit(q_empty);
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_s(0);
+    for (int n = 0; n < total; ++n) {
+      if (n + 1 < total) issue_s(n + 1);
+      const int st = n & 1;
+      ptx::mbar_wait(p_full, n & 1);
+      ptx::mbar_wait(pv_empty, (n & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t sV = sKV + st * 2 * kTile + kTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 128 keys = 8 UMMA_K steps: P k-block (k >> 2), V rows 16 k .. 16 k + 15
+          const uint64_t ad = ptx::umma_smem_desc(sP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = ptx::umma_smem_desc(sV + k * 2048, kTile, 1024);
+          ptx::umma_bf16(tmem_base + 128, ad, bd, idesc_pv, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(pv_full);
+        ptx::umma_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int sw = warp - 2, quad = warp & 3, hf = sw >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const Drop dc = make_drop(drop_p, seed_ptr, op_id);
+    const float sc2 = scale * kLog2e;
+    const uint32_t kq4 = (uint32_t)((Lk + 3) >> 2);
+    int n = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int b = it / H, h = it - b * H;
+      const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
+      float m = -INFINITY, l = 0.f;
+      float o[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) o[k] = 0.f;
+      for (int t = 0; t < nkb; ++t, ++n) {
+        const int kvalid = min(128, Lk - t * 128);
+        ptx::mbar_wait(s_full, n & 1);
+        ptx::tc_fence_after();
+        // pass 1: row maximum over the whole 128-key block (raw logits; sc2 > 0)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+        const float m_new = fmaxf(m, mx * sc2);
+        const float corr = ex2(m - m_new);     // first block: exp2(-inf) = 0
+        m = m_new;
+        l *= corr;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] *= corr;
+        // pass 2: this thread's 64 keys -> probabilities -> dropout -> bf16 P tile
+        float lsum = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + hf * 64 + cc * 32, r);
+          ptx::tmem_ld_wait();
+          if (cc == 1) {   // S is in registers: the tensor core may overwrite it with the next block's logits
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(s_empty);
+          }
+          const int j0 = hf * 64 + cc * 32;     // key offset inside the block
+          uint32_t pk[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = j0 + g * 4 + e;
+              p[e] = jj < kvalid ? ex2(fmaf(__uint_as_float(r[g * 4 + e]), sc2, -m)) : 0.f;
+              lsum += p[e];
+            }
+            if (dc.thr) {
+              const uint32_t hsh = quad_hash(dc, rowbase, (uint32_t)((t * 128 + j0) >> 2) + g);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) p[e] = ((hsh >> (8 * e)) & 0xffu) >= dc.thr ? p[e] * dc.scale : 0.f;
+            }
+            pk[2 * g] = pack2(p[0], p[1]);
+            pk[2 * g + 1] = pack2(p[2], p[3]);
+          }
+          const uint32_t prow = sP + hf * kTile;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(prow + tile_off(row, cc * 4 + c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        l += lsum;
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_full);
+        // O += P V  (this block's product, 32 of the 64 head-dim columns)
+        ptx::mbar_wait(pv_full, n & 1);
+        ptx::tc_fence_after();
+        {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + 128 + hf * 32, r);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(pv_empty);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(r[k]);
+        }
+      }
+      // ---- row sum: the two threads of a row exchange their halves
+      if (hf == 1) xl[row] = l;
+      named_bar(1 + quad, 64);
+      float tot = 0.f;
+      if (hf == 0) { tot = l + xl[row]; xl[row] = tot; }
+      named_bar(1 + quad, 64);
+      if (hf == 1) tot = xl[row];
+      if (row < Lq) {
+        const float inv = 1.f / tot;
+        bf16 *op = O + ((size_t)b * Lq + row) * ldo + h * HD + hf * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack2(o[8 * c] * inv, o[8 * c + 1] * inv);
+          v.y = pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+          v.z = pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+          v.w = pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+          *reinterpret_cast<uint4 *>(op + 8 * c) = v;
+        }
+        if (hf == 0) LSE[(size_t)it * Lq + row] = m + log2f(tot);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// =================================================================================================== backward
+// CTA = 18 warps, one per SM, persistent over (sample, head) items: warp 0 TMA, warp 1 MMA, warps 2..17 compute
+// (thread = one query row x 32 of the 128 keys of the block).  TMEM: S 0..127, dP 128..255, dV 256..319, dK 320..383,
+// dQ 384..447.  Per (item, key block):
+//   MMA      S = Q K^T, dP = dO V^T                                         (issued one block ahead)
+//   compute  P = exp2(S sc - lse), dS = P (drop(dP) - delta) scale  ->  bf16 P / dS tiles in shared memory
+//   MMA      dV = P^T dO, dK = dS^T Q   (flushed every key block: all Lq <= 128 queries are in this block)
+//            dQ += dS K                 (accumulates over the key blocks of the item)
+//   compute  flush of block n-1 (TMEM -> registers -> global) rides between the arithmetic and the tile stores of
+//            block n, so the tensor pipe always has the next group queued.
+constexpr int kBwdThreads = 576;
+constexpr int kBOffQdO = 0, kBOffKV = 4 * kTile, kBOffP = 8 * kTile, kBOffdS = 10 * kTile, kBOffBar = 12 * kTile;
+constexpr int kBwdSmem = kBOffBar + 256;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const bf16 *__restrict__ O, int ldo, const float *__restrict__ LSE, bf16 *__restrict__ dQ, int lddq,
+                   bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, int n_items,
+                   float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_s = ptx::smem_u32(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kBOffBar);
+  uint64_t *qdo_full = bars + 0, *qdo_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 6, *sdp_full = bars + 8,
+           *sdp_empty = bars + 9, *pds_full = bars + 10, *acc_full = bars + 11, *acc_empty = bars + 12;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (Lk + 127) >> 7;
+
+  if (threadIdx.x == 0 && (smem_s & 1023u)) __trap();
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&qdo_full[s], 1); ptx::mbar_init(&qdo_empty[s], 1);
+        ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1);
+      }
+      ptx::mbar_init(sdp_full, 1); ptx::mbar_init(sdp_empty, 16); ptx::mbar_init(pds_full, 16);
+      ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, 16);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQdO = smem_s + kBOffQdO, sKV = smem_s + kBOffKV, sP = smem_s + kBOffP, sdS = smem_s + kBOffdS;
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_items > 0 ? my_items * nkb : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int n = 0, j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      const int b = it / H, h = it - b * H, qs = j & 1;
+      ptx::mbar_wait(&qdo_empty[qs], ((j >> 1) & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&qdo_full[qs], 2 * kTile);
+        tma_load_3d(sQdO + qs * 2 * kTile, &tmQ, &qdo_full[qs], h * HD, 0, b);
+        tma_load_3d(sQdO + qs * 2 * kTile + kTile, &tmdO, &qdo_full[qs], h * HD, 0, b);
+      }
+      __syncwarp();
+      for (int t = 0; t < nkb; ++t, ++n) {
+        const int st = n & 1;
+        ptx::mbar_wait(&kv_empty[st], ((n >> 1) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+          tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
+          tma_load_3d(sKV + st * 2 * kTile + kTile, &tmV, &kv_full[st], h * HD, t * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_t = ptx::umma_idesc_bf16(128, 64, 1, 1);    // A = P / dS transposed (MN-major), B MN-major
+    const uint32_t idesc_q = ptx::umma_idesc_bf16(128, 64, 0, 1);    // A = dS K-major, B = K MN-major
+    auto issue_sdp = [&](int n) {
+      const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      if (t == 0) ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
+      ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
+      ptx::mbar_wait(sdp_empty, (n & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t q_s = sQdO + qs * 2 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile, v_s = k_s + kTile;
+        mma_kmajor_kmajor(tmem_base, q_s, k_s, 4, idesc_s, false);          // S  = Q K^T
+        mma_kmajor_kmajor(tmem_base + 128, do_s, v_s, 4, idesc_s, false);   // dP = dO V^T
+        ptx::umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_sdp(0);
+    for (int n = 0; n < total; ++n) {
+      if (n + 1 < total) issue_sdp(n + 1);
+      const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      ptx::mbar_wait(pds_full, n & 1);
+      ptx::mbar_wait(acc_empty, (n & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t q_s = sQdO + qs * 2 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // K = 128 queries: MN-major A advances 16 rows = 2048 B per step
+          const uint64_t ap = ptx::umma_smem_desc(sP + k * 2048, kTile, 1024);
+          const uint64_t as = ptx::umma_smem_desc(sdS + k * 2048, kTile, 1024);
+          const uint64_t bo = ptx::umma_smem_desc(do_s + k * 2048, kTile, 1024);
+          const uint64_t bq = ptx::umma_smem_desc(q_s + k * 2048, kTile, 1024);
+          ptx::umma_bf16(tmem_base + 256, ap, bo, idesc_t, k > 0 ? 1u : 0u);   // dV = P^T dO
+          ptx::umma_bf16(tmem_base + 320, as, bq, idesc_t, k > 0 ? 1u : 0u);   // dK = dS^T Q
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // K = 128 keys: dS K-major k-block (k >> 2), K rows 16 k ..
+          const uint64_t ad = ptx::umma_smem_desc(sdS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+          const uint64_t bk = ptx::umma_smem_desc(k_s + k * 2048, kTile, 1024);
+          ptx::umma_bf16(tmem_base + 384, ad, bk, idesc_q, (t > 0 || k > 0) ? 1u : 0u);   // dQ += dS K
+        }
+        ptx::umma_commit(acc_full);
+        ptx::umma_commit(&kv_empty[st]);
+        if (t == nkb - 1) ptx::umma_commit(&qdo_empty[qs]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int cw = warp - 2, quad = warp & 3, qt = cw >> 2;     // qt: which 32 of the block's 128 keys
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const Drop dc = make_drop(drop_p, seed_ptr, op_id);
+    const float sc2 = scale * kLog2e;
+    const uint32_t kq4 = (uint32_t)((Lk + 3) >> 2);
+    // flush of one finished block: dV, dK (rows = keys of that block) and, at the end of an item, dQ (rows = queries)
+    auto flush = [&](int fn) {
+      const int ft = fn % nkb, fj = fn / nkb;
+      const int fit = (int)blockIdx.x + fj * (int)gridDim.x;
+      const int fb = fit / H, fh = fit - fb * H;
+      ptx::mbar_wait(acc_full, fn & 1);
+      ptx::tc_fence_after();
+      uint32_t rv[16], rk[16], rq[16];
+      tmem_ld16(t_row + 256 + qt * 16, rv);
+      tmem_ld16(t_row + 320 + qt * 16, rk);
+      const bool last = ft == nkb - 1;
+      if (last) tmem_ld16(t_row + 384 + qt * 16, rq);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
+      const int key = ft * 128 + row;
+      if (key < Lk) {
+        bf16 *pk = dK + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16;
+        bf16 *pv = dV + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16;
+        uint4 a, c;
+        a.x = pack2(__uint_as_float(rk[0]), __uint_as_float(rk[1])); a.y = pack2(__uint_as_float(rk[2]), __uint_as_float(rk[3]));
+        a.z = pack2(__uint_as_float(rk[4]), __uint_as_float(rk[5])); a.w = pack2(__uint_as_float(rk[6]), __uint_as_float(rk[7]));
+        c.x = pack2(__uint_as_float(rk[8]), __uint_as_float(rk[9])); c.y = pack2(__uint_as_float(rk[10]), __uint_as_float(rk[11]));
+        c.z = pack2(__uint_as_float(rk[12]), __uint_as_float(rk[13])); c.w = pack2(__uint_as_float(rk[14]), __uint_as_float(rk[15]));
+        reinterpret_cast<uint4 *>(pk)[0] = a; reinterpret_cast<uint4 *>(pk)[1] = c;
+        a.x = pack2(__uint_as_float(rv[0]), __uint_as_float(rv[1])); a.y = pack2(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+        a.z = pack2(__uint_as_float(rv[4]), __uint_as_float(rv[5])); a.w = pack2(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+        c.x = pack2(__uint_as_float(rv[8]), __uint_as_float(rv[9])); c.y = pack2(__uint_as_float(rv[10]), __uint_as_float(rv[11]));
+        c.z = pack2(__uint_as_float(rv[12]), __uint_as_float(rv[13])); c.w = pack2(__uint_as_float(rv[14]), __uint_as_float(rv[15]));
+        reinterpret_cast<uint4 *>(pv)[0] = a; reinterpret_cast<uint4 *>(pv)[1] = c;
+      }
+      if (last && row < Lq) {
+        bf16 *pq = dQ + ((size_t)fb * Lq + row) * lddq + fh * HD + qt * 16;
+        uint4 a, c;
+        a.x = pack2(__uint_as_float(rq[0]), __uint_as_float(rq[1])); a.y = pack2(__uint_as_float(rq[2]), __uint_as_float(rq[3]));
+        a.z = pack2(__uint_as_float(rq[4]), __uint_as_float(rq[5])); a.w = pack2(__uint_as_float(rq[6]), __uint_as_float(rq[7]));
+        c.x = pack2(__uint_as_float(rq[8]), __uint_as_float(rq[9])); c.y = pack2(__uint_as_float(rq[10]), __uint_as_float(rq[11]));
+        c.z = pack2(__uint_as_float(rq[12]), __uint_as_float(rq[13])); c.w = pack2(__uint_as_float(rq[14]), __uint_as_float(rq[15]));
+        reinterpret_cast<uint4 *>(pq)[0] = a; reinterpret_cast<uint4 *>(pq)[1] = c;
+      }
+    };
+    int n = 0, j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      const int b = it / H, h = it - b * H, qs = j & 1;
+      const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
+      // per-row constants of the item: lse (log2 units) and delta = sum_d dO[i, d] O[i, d]
+      float lse = INFINITY, delta = 0.f;     // rows >= Lq: p = exp2(-inf) = 0, dS = 0
+      ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
+      if (row < Lq) {
+        lse = __ldg(LSE + (size_t)it * Lq + row);
+        const uint4 *po = reinterpret_cast<const uint4 *>(O + ((size_t)b * Lq + row) * ldo + h * HD);
+        const uint32_t do_s = sQdO + qs * 2 * kTile + kTile;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = __ldg(po + c), d = lds128(do_s + tile_off(row, c));
+          const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = __bfloat1622float2(ha[q]), fd = __bfloat1622float2(hd[q]);
+            delta = fmaf(fa.x, fd.x, delta);
+            delta = fmaf(fa.y, fd.y, delta);
+          }
+        }
+      }
+      for (int t = 0; t < nkb; ++t, ++n) {
+        const int kvalid = min(128, Lk - t * 128);
+        ptx::mbar_wait(sdp_full, n & 1);
+        ptx::tc_fence_after();
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32(t_row + qt * 32, rs);
+        ptx::tmem_ld_32x32(t_row + 128 + qt * 32, rp);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(sdp_empty);     // S / dP are in registers: the next block's may be issued
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float p[4], ds[4];
+          uint32_t hsh = 0;
+          if (dc.thr) hsh = quad_hash(dc, rowbase, (uint32_t)((t * 128 + qt * 32) >> 2) + g);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = qt * 32 + g * 4 + e;
+            const float pe = jj < kvalid ? ex2(fmaf(__uint_as_float(rs[g * 4 + e]), sc2, -lse)) : 0.f;
+            float dpe = __uint_as_float(rp[g * 4 + e]);
+            float pdrop = pe;
+            if (dc.thr) {
+              const bool keep = ((hsh >> (8 * e)) & 0xffu) >= dc.thr;
+              pdrop = keep ? pe * dc.scale : 0.f;
+              dpe = keep ? dpe * dc.scale : 0.f;
+            }
+            p[e] = pdrop;
+            ds[e] = pe * (dpe - delta) * scale;
+          }
+          pp[2 * g] = pack2(p[0], p[1]); pp[2 * g + 1] = pack2(p[2], p[3]);
+          pd[2 * g] = pack2(ds[0], ds[1]); pd[2 * g + 1] = pack2(ds[2], ds[3]);
+        }
+        // the P / dS tiles are free once the MMA group of block n-1 has retired; flush that block on the way
+        if (n > 0) flush(n - 1);
+        const uint32_t kb = (uint32_t)(qt >> 1) * kTile, c0 = (qt & 1) * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          sts128(sP + kb + tile_off(row, c0 + c), pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+          sts128(sdS + kb + tile_off(row, c0 + c), pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(pds_full);
+      }
+    }
+    if (total > 0) flush(total - 1);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// [B][L][H*64] bf16 view with row stride ld elements; box = 64 channels x 128 tokens x 1 sample, 128B swizzle
+static int make_map3(CUtensorMap *m, const void *base, int B, int L, int H, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VPF_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7))
+    return fail(VPF_EINVAL, "attention operand must be 16-byte aligned with a row stride that is a multiple of 8 (ld=%d)", ld);
+  cuuint64_t dims[3] = {(cuuint64_t)H * HD, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+  cuuint32_t box[3] = {HD, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VPF_ECUDA, "cuTensorMapEncodeTiled (attention) failed (%d) B=%d L=%d H=%d ld=%d", (int)r, B, L, H, ld);
+  return VPF_OK;
+}
+
+int attention_tc_fwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, void *O, int ldo, float *LSE, int B,
+                     int H, int Lq, int Lk, float scale, float drop_p, const unsigned long long *seed_ptr,
+                     unsigned int op_id, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  VPF_TRY(make_map3(&tq, Q, B, Lq, H, ldq));
+  VPF_TRY(make_map3(&tk, K, B, Lk, H, ldkv));
+  VPF_TRY(make_map3(&tv, V, B, Lk, H, ldkv));
+  static bool attr = false;
+  if (!attr) {
+    VPF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    attr = true;
+  }
+  const int items = B * H;
+  const int grid = min(items, 2 * num_sms());
+  attn_tc_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, (bf16 *)O, ldo, LSE, H, Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
+  return check_launch("attn_tc_fwd_kernel");
+}
+
+int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, const void *O, int ldo, const void *dO,
+                     int lddo, const float *LSE, void *dQ, int lddq, void *dK, void *dV, int lddkv, int B, int H, int Lq,
+                     int Lk, float scale, float drop_p, const unsigned long long *seed_ptr, unsigned int op_id,
+                     cudaStream_t st) {
+  CUtensorMap tq, tk, tv, tdo;
+  VPF_TRY(make_map3(&tq, Q, B, Lq, H, ldq));
+  VPF_TRY(make_map3(&tk, K, B, Lk, H, ldkv));
+  VPF_TRY(make_map3(&tv, V, B, Lk, H, ldkv));
+  VPF_TRY(make_map3(&tdo, dO, B, Lq, H, lddo));
+  VPF_REQUIRE((lddq & 7) == 0 && (lddkv & 7) == 0 && (ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(dQ) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(dK) & 15) == 0 && (reinterpret_cast<uintptr_t>(dV) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(O) & 15) == 0, "attention_bwd (tcgen05): outputs must be 16-byte aligned, strides multiples of 8");
+  static bool attr = false;
+  if (!attr) {
+    VPF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    attr = true;
+  }
+  const int items = B * H;
+  const int grid = min(items, num_sms());
+  attn_tc_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, (const bf16 *)O, ldo, LSE, (bf16 *)dQ, lddq, (bf16 *)dK,
+                                                           (bf16 *)dV, lddkv, H, Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
+  return check_launch("attn_tc_bwd_kernel");
+}
+
+}  // namespace atc
+}  // namespace vpf

@@ -68,6 +68,7 @@ def _dev(device):
 def manual_seed(seed, device=None):
     """Seed the counter-based dropout stream (the backward pass regenerates masks from the same seed)."""
     StepState.get(_dev(device))[1] = int(seed) & 0x7FFFFFFFFFFFFFFF
+    _EPOCH[0] = 0
 
 
 def advance_dropout_seed(device=None):
