@@ -47,6 +47,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// producer-side wait: the TMA warp is never on the critical path (two stages of look-ahead), so it backs off instead of
+// burning issue slots of the softmax warps in a try_wait spin
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -81,6 +86,16 @@ __device__ __forceinline__ Drop make_drop(float p, const unsigned long long *see
   d.scale = d.thr ? 256.f / (256.f - (float)d.thr) : 1.f;
   return d;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+// bit 7 of byte e set <=> byte e of the hash is < thr (element e is DROPPED); exact for thr <= 128 (SWAR, no borrows:
+// every byte of kthr = 0x7f + thr is >= the 7-bit value subtracted from it)
+__device__ __forceinline__ uint32_t drop_bits(uint32_t hsh, uint32_t kthr) {
+  return (kthr - (hsh & 0x7f7f7f7fu)) & ~hsh & 0x80808080u;
+}
 // hash of the 4-key group g4 (= j >> 2) of row `rowbase` (= (bh * Lq + i) * ceil(Lk / 4))
 __device__ __forceinline__ uint32_t quad_hash(const Drop &dc, uint32_t rowbase, uint32_t g4) {
   return rng::mix32((rowbase + g4) * 0x9e3779b1u ^ dc.key);
@@ -99,12 +114,31 @@ __device__ __forceinline__ void mma_kmajor_kmajor(uint32_t tmem_d, uint32_t a_s,
 
 // =================================================================================================== forward
 // CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax (thread = one query row x one 64-key half
-// of the 128-key block; O columns split the same way).  Two CTAs per SM (112.6 KB shared memory, 256 TMEM columns each).
-// Persistent over (sample, head) items; key blocks of 128 stream through a 2-stage K/V ring.
+// of the 128-key block).  Two CTAs per SM (112.6 KB shared memory, 256 TMEM columns each), persistent over
+// (sample, head) items; key blocks of 128 stream through a 2-stage K/V ring.
+// O stays in TMEM: the P.V products of all key blocks of an item accumulate there (tcgen05.mma accumulate), the softmax
+// threads keep only the running (max, sum) of their row.  The running max is LAZY: a row switches to a larger reference
+// only when the block maximum exceeds the current one by more than 2^8 (probabilities up to 256 are harmless in fp32 /
+// bf16), and only then is that row of O rescaled in TMEM (tcgen05.ld -> multiply -> tcgen05.st) -- after the first key
+// block of a 2048-point cross-attention this almost never happens.  Softmax arithmetic per logit: max, fma, ex2, add,
+// 3 for the dropout bit, half a pack; the 1 / (1 - p) of dropout is folded into the final normalisation.
 constexpr int kFwdThreads = 320;
 constexpr int kFOffQ = 0, kFOffKV = kTile, kFOffP = kFOffKV + 4 * kTile, kFOffX = kFOffP + 2 * kTile, kFOffBar = kFOffX + 512;
-constexpr int kFwdSmem = kFOffBar + 128;
+constexpr int kFwdSmem = kFOffBar + 96;
 static_assert(kFwdSmem <= 115712, "two forward CTAs per SM");
+constexpr float kLazy = 8.f;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -115,9 +149,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t smem_s = ptx::smem_u32(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFOffBar);
   uint64_t *q_full = bars + 0, *q_empty = bars + 1, *kv_full = bars + 2, *kv_empty = bars + 4, *s_full = bars + 6,
-           *s_empty = bars + 7, *p_full = bars + 8, *pv_full = bars + 9, *pv_empty = bars + 10;
+           *s_empty = bars + 7, *p_full = bars + 8, *pv_full = bars + 9, *o_empty = bars + 10;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
-  float *xl = reinterpret_cast<float *>(smem + kFOffX);
+  __nv_bfloat16 *xm = reinterpret_cast<__nv_bfloat16 *>(smem + kFOffX);   // [2][128] block-max bounds of the two halves
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (Lk + 127) >> 7;
 
@@ -130,7 +164,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
       for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
       ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, 8); ptx::mbar_init(p_full, 8);
-      ptx::mbar_init(pv_full, 1); ptx::mbar_init(pv_empty, 8);
+      ptx::mbar_init(pv_full, 1); ptx::mbar_init(o_empty, 8);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -148,7 +182,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
       const int b = it / H, h = it - b * H;
-      ptx::mbar_wait(q_empty, (j & 1) ^ 1);
+      mbar_wait_backoff(q_empty, (j & 1) ^ 1);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(q_full, kTile);
         tma_load_3d(sQ, &tmQ, q_full, h * HD, 0, b);
@@ -156,7 +190,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       for (int t = 0; t < nkb; ++t, ++n) {
         const int st = n & 1;
-        ptx::mbar_wait(&kv_empty[st], ((n >> 1) & 1) ^ 1);
+        mbar_wait_backoff(&kv_empty[st], ((n >> 1) & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
           tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
@@ -167,17 +201,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0), idesc_pv = ptx::umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 64, 0, 1);
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total = my_items * nkb;
     auto issue_s = [&](int n) {
       const int t = n % nkb, j = n / nkb, st = n & 1;
+      const int kv16 = (min(128, Lk - t * 128) + 15) & ~15;     // valid keys of this block, rounded up to the UMMA N step
       if (t == 0) ptx::mbar_wait(q_full, j & 1);
       ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
       ptx::mbar_wait(s_empty, (n & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        mma_kmajor_kmajor(tmem_base, sQ, sKV + st * 2 * kTile, 4, idesc_s, false);
+        mma_kmajor_kmajor(tmem_base, sQ, sKV + st * 2 * kTile, 4, ptx::umma_idesc_bf16(128, kv16, 0, 0), false);
         ptx::umma_commit(s_full);
         if (t == nkb - 1) ptx::umma_commit(q_empty);
       }
@@ -186,17 +221,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (total > 0) issue_s(0);
     for (int n = 0; n < total; ++n) {
       if (n + 1 < total) issue_s(n + 1);
-      const int st = n & 1;
+      const int t = n % nkb, j = n / nkb, st = n & 1;
+      const int ksteps = (min(128, Lk - t * 128) + 15) >> 4;
       ptx::mbar_wait(p_full, n & 1);
-      ptx::mbar_wait(pv_empty, (n & 1) ^ 1);
+      if (t == 0) ptx::mbar_wait(o_empty, (j & 1) ^ 1);      // the previous item's O has been read out of TMEM
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t sV = sKV + st * 2 * kTile + kTile;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // 128 keys = 8 UMMA_K steps: P k-block (k >> 2), V rows 16 k .. 16 k + 15
-          const uint64_t ad = ptx::umma_smem_desc(sP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = ptx::umma_smem_desc(sV + k * 2048, kTile, 1024);
-          ptx::umma_bf16(tmem_base + 128, ad, bd, idesc_pv, k > 0 ? 1u : 0u);
+          if (k < ksteps) {
+            const uint64_t ad = ptx::umma_smem_desc(sP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+            const uint64_t bd = ptx::umma_smem_desc(sV + k * 2048, kTile, 1024);
+            ptx::umma_bf16(tmem_base + 128, ad, bd, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+          }
         }
         ptx::umma_commit(pv_full);
         ptx::umma_commit(&kv_empty[st]);
@@ -211,105 +249,122 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const Drop dc = make_drop(drop_p, seed_ptr, op_id);
     const float sc2 = scale * kLog2e;
     const uint32_t kq4 = (uint32_t)((Lk + 3) >> 2);
-    int n = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const uint32_t prow = sP + hf * kTile;
+    const uint32_t kthr = 0x7f7f7f7fu + dc.thr * 0x01010101u;
+    int n = 0, j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
       const int b = it / H, h = it - b * H;
       const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
-      float m = -INFINITY, l = 0.f;
-      float o[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] = 0.f;
+      float m = 0.f, l = 0.f;
       for (int t = 0; t < nkb; ++t, ++n) {
         const int kvalid = min(128, Lk - t * 128);
+        const int j0 = hf * 64;                         // this thread's key offset inside the block
         ptx::mbar_wait(s_full, n & 1);
         ptx::tc_fence_after();
-        // pass 1: row maximum over the whole 128-key block (raw logits; sc2 > 0)
+        uint32_t s0[32], s1[32];
+        ptx::tmem_ld_32x32(t_row + j0, s0);
+        ptx::tmem_ld_32x32(t_row + j0 + 32, s1);
+        ptx::tmem_ld_wait();
+        // block maximum of this half (raw logits; sc2 > 0), exchanged with the other half as a bf16 UPPER bound
         float mx = -INFINITY;
+        if (kvalid == 128) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + c * 32, r);
-          ptx::tmem_ld_wait();
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])));
+        } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(r[e]));
-        }
-        const float m_new = fmaxf(m, mx * sc2);
-        const float corr = ex2(m - m_new);     // first block: exp2(-inf) = 0
-        m = m_new;
-        l *= corr;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) o[k] *= corr;
-        // pass 2: this thread's 64 keys -> probabilities -> dropout -> bf16 P tile
-        float lsum = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + hf * 64 + cc * 32, r);
-          ptx::tmem_ld_wait();
-          if (cc == 1) {   // S is in registers: the tensor core may overwrite it with the next block's logits
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(s_empty);
+          for (int e = 0; e < 32; ++e) {
+            if (j0 + e < kvalid) mx = fmaxf(mx, __uint_as_float(s0[e]));
+            if (j0 + 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(s1[e]));
           }
-          const int j0 = hf * 64 + cc * 32;     // key offset inside the block
-          uint32_t pk[16];
+        }
+        mx *= sc2;
+        const float bound = mx + fabsf(mx) * 0.0078125f;          // >= mx after round-to-nearest to 8 mantissa bits
+        xm[hf * 128 + row] = __float2bfloat16(mx == -INFINITY ? -1e30f : bound);
+        named_bar(1 + quad, 64);
+        const float m_blk = fmaxf(__bfloat162float(xm[row]), __bfloat162float(xm[128 + row]));
+        // S is in registers: the next block's logits may be issued.  (Arriving only AFTER the exchange read also orders
+        // the next block's xm writes -- which need the next s_full -- behind this block's xm reads.)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty);
+        bool need = t == 0 ? false : (m_blk > m + kLazy);
+        if (t == 0) m = m_blk;
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale this row of O in TMEM (the previous P.V must have retired) and the running sum
+          const float m_new = need ? m_blk : m;
+          const float corr = ex2(m - m_new);
+          ptx::mbar_wait(pv_full, (n - 1) & 1);
+          ptx::tc_fence_after();
+          uint32_t o[32];
+          ptx::tmem_ld_32x32(t_row + 128 + hf * 32, o);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float p[4];
+          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * corr);
+          tmem_st32(t_row + 128 + hf * 32, o);
+          tmem_st_wait();
+          l *= corr;
+          m = m_new;
+        }
+        // probabilities -> dropout -> bf16 P tile (written once the previous P.V has finished reading the tile)
+        if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+        float lsum = 0.f;
+        const float negm = -m;
+        const uint32_t g4 = (uint32_t)((t * 128 + j0) >> 2);
+        auto half = [&](const uint32_t (&sx)[32], int hh, bool tail) {   // 32 keys: 4 chunks of 8
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = j0 + g * 4 + e;
-              p[e] = jj < kvalid ? ex2(fmaf(__uint_as_float(r[g * 4 + e]), sc2, -m)) : 0.f;
+          for (int c = 0; c < 4; ++c) {
+            float p[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              p[e] = ex2(fmaf(__uint_as_float(sx[c * 8 + e]), sc2, negm));
+              if (tail && j0 + hh * 32 + c * 8 + e >= kvalid) p[e] = 0.f;
               lsum += p[e];
             }
+            uint32_t w0 = pack2(p[0], p[1]), w1 = pack2(p[2], p[3]), w2 = pack2(p[4], p[5]), w3 = pack2(p[6], p[7]);
             if (dc.thr) {
-              const uint32_t hsh = quad_hash(dc, rowbase, (uint32_t)((t * 128 + j0) >> 2) + g);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) p[e] = ((hsh >> (8 * e)) & 0xffu) >= dc.thr ? p[e] * dc.scale : 0.f;
+              const uint32_t d0 = drop_bits(quad_hash(dc, rowbase, g4 + hh * 8 + c * 2), kthr);
+              const uint32_t d1 = drop_bits(quad_hash(dc, rowbase, g4 + hh * 8 + c * 2 + 1), kthr);
+              w0 &= ~prmt(d0, 0x9988u); w1 &= ~prmt(d0, 0xbbaau);
+              w2 &= ~prmt(d1, 0x9988u); w3 &= ~prmt(d1, 0xbbaau);
             }
-            pk[2 * g] = pack2(p[0], p[1]);
-            pk[2 * g + 1] = pack2(p[2], p[3]);
+            sts128(prow + tile_off(row, hh * 4 + c), w0, w1, w2, w3);
           }
-          const uint32_t prow = sP + hf * kTile;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            sts128(prow + tile_off(row, cc * 4 + c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        }
+        };
+        if (kvalid == 128) { half(s0, 0, false); half(s1, 1, false); }
+        else { half(s0, 0, true); half(s1, 1, true); }
         l += lsum;
+        ptx::tc_fence_before();
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_full);
-        // O += P V  (this block's product, 32 of the 64 head-dim columns)
-        ptx::mbar_wait(pv_full, n & 1);
-        ptx::tc_fence_after();
-        {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + 128 + hf * 32, r);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(pv_empty);
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(r[k]);
-        }
       }
-      // ---- row sum: the two threads of a row exchange their halves
-      if (hf == 1) xl[row] = l;
+      // ---- end of the item: read O, normalise, store
+      ptx::mbar_wait(pv_full, (n - 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(t_row + 128 + hf * 32, o);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_empty);
+      // row sum: the two threads of a row exchange their halves through 4 bytes of the row's own (now idle) P segment
+      float *xl = reinterpret_cast<float *>(smem + kFOffP + row * 128);
+      if (hf == 1) *xl = l;
       named_bar(1 + quad, 64);
       float tot = 0.f;
-      if (hf == 0) { tot = l + xl[row]; xl[row] = tot; }
+      if (hf == 0) { tot = l + *xl; *xl = tot; }
       named_bar(1 + quad, 64);
-      if (hf == 1) tot = xl[row];
+      if (hf == 1) tot = *xl;
       if (row < Lq) {
-        const float inv = 1.f / tot;
+        const float inv = dc.scale / tot;
         bf16 *op = O + ((size_t)b * Lq + row) * ldo + h * HD + hf * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
-          v.x = pack2(o[8 * c] * inv, o[8 * c + 1] * inv);
-          v.y = pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-          v.z = pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-          v.w = pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+          v.x = pack2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          v.y = pack2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          v.z = pack2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          v.w = pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
           *reinterpret_cast<uint4 *>(op + 8 * c) = v;
         }
         if (hf == 0) LSE[(size_t)it * Lq + row] = m + log2f(tot);
@@ -329,16 +384,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   compute  P = exp2(S sc - lse), dS = P (drop(dP) - delta) scale  ->  bf16 P / dS tiles in shared memory
 //   MMA      dV = P^T dO, dK = dS^T Q   (flushed every key block: all Lq <= 128 queries are in this block)
 //            dQ += dS K                 (accumulates over the key blocks of the item)
-//   compute  flush of block n-1 (TMEM -> registers -> global) rides between the arithmetic and the tile stores of
-//            block n, so the tensor pipe always has the next group queued.
+//   compute  flush of block n-1 (TMEM -> registers -> global) rides behind the tile stores of block n, so the tensor
+//            pipe always has the next group queued.
+// Q, dO and O arrive together by TMA (delta = rowsum(dO o O) is computed from the shared-memory tiles); the 1 / (1 - p)
+// of dropout is folded into delta, the logit scale and the dV flush.
 constexpr int kBwdThreads = 576;
-constexpr int kBOffQdO = 0, kBOffKV = 4 * kTile, kBOffP = 8 * kTile, kBOffdS = 10 * kTile, kBOffBar = 12 * kTile;
+constexpr int kBOffQdO = 0, kBOffKV = 6 * kTile, kBOffP = 10 * kTile, kBOffdS = 12 * kTile, kBOffBar = 14 * kTile;
 constexpr int kBwdSmem = kBOffBar + 256;
+static_assert(kBwdSmem <= 232448, "backward shared memory");
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                   const bf16 *__restrict__ O, int ldo, const float *__restrict__ LSE, bf16 *__restrict__ dQ, int lddq,
+                   const __grid_constant__ CUtensorMap tmO, const float *__restrict__ LSE, bf16 *__restrict__ dQ, int lddq,
                    bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, int n_items,
                    float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -352,7 +410,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0 && (smem_s & 1023u)) __trap();
   if (warp == 0 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmO);
   }
   if (warp == 1) {
     if (ptx::elect_one()) {
@@ -381,16 +439,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
       const int b = it / H, h = it - b * H, qs = j & 1;
-      ptx::mbar_wait(&qdo_empty[qs], ((j >> 1) & 1) ^ 1);
+      mbar_wait_backoff(&qdo_empty[qs], ((j >> 1) & 1) ^ 1);
       if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&qdo_full[qs], 2 * kTile);
-        tma_load_3d(sQdO + qs * 2 * kTile, &tmQ, &qdo_full[qs], h * HD, 0, b);
-        tma_load_3d(sQdO + qs * 2 * kTile + kTile, &tmdO, &qdo_full[qs], h * HD, 0, b);
+        ptx::mbar_arrive_expect_tx(&qdo_full[qs], 3 * kTile);
+        tma_load_3d(sQdO + qs * 3 * kTile, &tmQ, &qdo_full[qs], h * HD, 0, b);
+        tma_load_3d(sQdO + qs * 3 * kTile + kTile, &tmdO, &qdo_full[qs], h * HD, 0, b);
+        tma_load_3d(sQdO + qs * 3 * kTile + 2 * kTile, &tmO, &qdo_full[qs], h * HD, 0, b);
       }
       __syncwarp();
       for (int t = 0; t < nkb; ++t, ++n) {
         const int st = n & 1;
-        ptx::mbar_wait(&kv_empty[st], ((n >> 1) & 1) ^ 1);
+        mbar_wait_backoff(&kv_empty[st], ((n >> 1) & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
           tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
@@ -401,17 +460,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_t = ptx::umma_idesc_bf16(128, 64, 1, 1);    // A = P / dS transposed (MN-major), B MN-major
     const uint32_t idesc_q = ptx::umma_idesc_bf16(128, 64, 0, 1);    // A = dS K-major, B = K MN-major
     auto issue_sdp = [&](int n) {
       const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      const int kv16 = (min(128, Lk - t * 128) + 15) & ~15;
       if (t == 0) ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
       ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
       ptx::mbar_wait(sdp_empty, (n & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t q_s = sQdO + qs * 2 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile, v_s = k_s + kTile;
+        const uint32_t q_s = sQdO + qs * 3 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile, v_s = k_s + kTile;
+        const uint32_t idesc_s = ptx::umma_idesc_bf16(128, kv16, 0, 0);
         mma_kmajor_kmajor(tmem_base, q_s, k_s, 4, idesc_s, false);          // S  = Q K^T
         mma_kmajor_kmajor(tmem_base + 128, do_s, v_s, 4, idesc_s, false);   // dP = dO V^T
         ptx::umma_commit(sdp_full);
@@ -422,11 +482,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int n = 0; n < total; ++n) {
       if (n + 1 < total) issue_sdp(n + 1);
       const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      const int ksteps = (min(128, Lk - t * 128) + 15) >> 4;
       ptx::mbar_wait(pds_full, n & 1);
       ptx::mbar_wait(acc_empty, (n & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t q_s = sQdO + qs * 2 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile;
+        const uint32_t q_s = sQdO + qs * 3 * kTile, do_s = q_s + kTile, k_s = sKV + st * 2 * kTile;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // K = 128 queries: MN-major A advances 16 rows = 2048 B per step
           const uint64_t ap = ptx::umma_smem_desc(sP + k * 2048, kTile, 1024);
@@ -437,10 +498,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           ptx::umma_bf16(tmem_base + 320, as, bq, idesc_t, k > 0 ? 1u : 0u);   // dK = dS^T Q
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // K = 128 keys: dS K-major k-block (k >> 2), K rows 16 k ..
-          const uint64_t ad = ptx::umma_smem_desc(sdS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
-          const uint64_t bk = ptx::umma_smem_desc(k_s + k * 2048, kTile, 1024);
-          ptx::umma_bf16(tmem_base + 384, ad, bk, idesc_q, (t > 0 || k > 0) ? 1u : 0u);   // dQ += dS K
+        for (int k = 0; k < 8; ++k) {   // K = the block's keys: dS K-major k-block (k >> 2), K rows 16 k ..
+          if (k < ksteps) {
+            const uint64_t ad = ptx::umma_smem_desc(sdS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+            const uint64_t bk = ptx::umma_smem_desc(k_s + k * 2048, kTile, 1024);
+            ptx::umma_bf16(tmem_base + 384, ad, bk, idesc_q, (t > 0 || k > 0) ? 1u : 0u);   // dQ += dS K
+          }
         }
         ptx::umma_commit(acc_full);
         ptx::umma_commit(&kv_empty[st]);
@@ -455,14 +518,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     const Drop dc = make_drop(drop_p, seed_ptr, op_id);
     const float sc2 = scale * kLog2e;
+    const float scale_d = scale * dc.scale, inv_dscale = 1.f / dc.scale;
     const uint32_t kq4 = (uint32_t)((Lk + 3) >> 2);
+    const uint32_t kthr = 0x7f7f7f7fu + dc.thr * 0x01010101u;
+    auto pack8 = [](const uint32_t *r, float f) {
+      uint4 a;
+      a.x = pack2(__uint_as_float(r[0]) * f, __uint_as_float(r[1]) * f); a.y = pack2(__uint_as_float(r[2]) * f, __uint_as_float(r[3]) * f);
+      a.z = pack2(__uint_as_float(r[4]) * f, __uint_as_float(r[5]) * f); a.w = pack2(__uint_as_float(r[6]) * f, __uint_as_float(r[7]) * f);
+      return a;
+    };
     // flush of one finished block: dV, dK (rows = keys of that block) and, at the end of an item, dQ (rows = queries)
     auto flush = [&](int fn) {
       const int ft = fn % nkb, fj = fn / nkb;
       const int fit = (int)blockIdx.x + fj * (int)gridDim.x;
       const int fb = fit / H, fh = fit - fb * H;
-      ptx::mbar_wait(acc_full, fn & 1);
-      ptx::tc_fence_after();
       uint32_t rv[16], rk[16], rq[16];
       tmem_ld16(t_row + 256 + qt * 16, rv);
       tmem_ld16(t_row + 320 + qt * 16, rk);
@@ -474,44 +543,29 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) ptx::mbar_arrive(acc_empty);
       const int key = ft * 128 + row;
       if (key < Lk) {
-        bf16 *pk = dK + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16;
-        bf16 *pv = dV + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16;
-        uint4 a, c;
-        a.x = pack2(__uint_as_float(rk[0]), __uint_as_float(rk[1])); a.y = pack2(__uint_as_float(rk[2]), __uint_as_float(rk[3]));
-        a.z = pack2(__uint_as_float(rk[4]), __uint_as_float(rk[5])); a.w = pack2(__uint_as_float(rk[6]), __uint_as_float(rk[7]));
-        c.x = pack2(__uint_as_float(rk[8]), __uint_as_float(rk[9])); c.y = pack2(__uint_as_float(rk[10]), __uint_as_float(rk[11]));
-        c.z = pack2(__uint_as_float(rk[12]), __uint_as_float(rk[13])); c.w = pack2(__uint_as_float(rk[14]), __uint_as_float(rk[15]));
-        reinterpret_cast<uint4 *>(pk)[0] = a; reinterpret_cast<uint4 *>(pk)[1] = c;
-        a.x = pack2(__uint_as_float(rv[0]), __uint_as_float(rv[1])); a.y = pack2(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
-        a.z = pack2(__uint_as_float(rv[4]), __uint_as_float(rv[5])); a.w = pack2(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
-        c.x = pack2(__uint_as_float(rv[8]), __uint_as_float(rv[9])); c.y = pack2(__uint_as_float(rv[10]), __uint_as_float(rv[11]));
-        c.z = pack2(__uint_as_float(rv[12]), __uint_as_float(rv[13])); c.w = pack2(__uint_as_float(rv[14]), __uint_as_float(rv[15]));
-        reinterpret_cast<uint4 *>(pv)[0] = a; reinterpret_cast<uint4 *>(pv)[1] = c;
+        uint4 *pk = reinterpret_cast<uint4 *>(dK + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16);
+        uint4 *pv = reinterpret_cast<uint4 *>(dV + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16);
+        pk[0] = pack8(rk, scale_d); pk[1] = pack8(rk + 8, scale_d);
+        pv[0] = pack8(rv, dc.scale); pv[1] = pack8(rv + 8, dc.scale);
       }
       if (last && row < Lq) {
-        bf16 *pq = dQ + ((size_t)fb * Lq + row) * lddq + fh * HD + qt * 16;
-        uint4 a, c;
-        a.x = pack2(__uint_as_float(rq[0]), __uint_as_float(rq[1])); a.y = pack2(__uint_as_float(rq[2]), __uint_as_float(rq[3]));
-        a.z = pack2(__uint_as_float(rq[4]), __uint_as_float(rq[5])); a.w = pack2(__uint_as_float(rq[6]), __uint_as_float(rq[7]));
-        c.x = pack2(__uint_as_float(rq[8]), __uint_as_float(rq[9])); c.y = pack2(__uint_as_float(rq[10]), __uint_as_float(rq[11]));
-        c.z = pack2(__uint_as_float(rq[12]), __uint_as_float(rq[13])); c.w = pack2(__uint_as_float(rq[14]), __uint_as_float(rq[15]));
-        reinterpret_cast<uint4 *>(pq)[0] = a; reinterpret_cast<uint4 *>(pq)[1] = c;
+        uint4 *pq = reinterpret_cast<uint4 *>(dQ + ((size_t)fb * Lq + row) * lddq + fh * HD + qt * 16);
+        pq[0] = pack8(rq, scale_d); pq[1] = pack8(rq + 8, scale_d);
       }
     };
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-      const int b = it / H, h = it - b * H, qs = j & 1;
+      const int qs = j & 1;
       const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
-      // per-row constants of the item: lse (log2 units) and delta = sum_d dO[i, d] O[i, d]
+      // per-row constants of the item: lse (log2 units) and delta' = sum_d dO[i, d] O[i, d] / dropout scale
       float lse = INFINITY, delta = 0.f;     // rows >= Lq: p = exp2(-inf) = 0, dS = 0
+      if (row < Lq) lse = __ldg(LSE + (size_t)it * Lq + row);
       ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
-      if (row < Lq) {
-        lse = __ldg(LSE + (size_t)it * Lq + row);
-        const uint4 *po = reinterpret_cast<const uint4 *>(O + ((size_t)b * Lq + row) * ldo + h * HD);
-        const uint32_t do_s = sQdO + qs * 2 * kTile + kTile;
+      {
+        const uint32_t do_s = sQdO + qs * 3 * kTile + kTile, o_s = do_s + kTile;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint4 a = __ldg(po + c), d = lds128(do_s + tile_off(row, c));
+          const uint4 a = lds128(o_s + tile_off(row, c)), d = lds128(do_s + tile_off(row, c));
           const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -520,6 +574,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             delta = fmaf(fa.y, fd.y, delta);
           }
         }
+        delta *= inv_dscale;
       }
       for (int t = 0; t < nkb; ++t, ++n) {
         const int kvalid = min(128, Lk - t * 128);
@@ -532,31 +587,32 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(sdp_empty);     // S / dP are in registers: the next block's may be issued
+        const float neglse = -lse;
         uint32_t pp[16], pd[16];
+        const uint32_t g4 = (uint32_t)((t * 128 + qt * 32) >> 2);
+        auto body = [&](bool tail) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float p[4], ds[4];
-          uint32_t hsh = 0;
-          if (dc.thr) hsh = quad_hash(dc, rowbase, (uint32_t)((t * 128 + qt * 32) >> 2) + g);
+          for (int g = 0; g < 8; ++g) {
+            float p[4], ds[4];
+            uint32_t db = 0;
+            if (dc.thr) db = drop_bits(quad_hash(dc, rowbase, g4 + g), kthr);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jj = qt * 32 + g * 4 + e;
-            const float pe = jj < kvalid ? ex2(fmaf(__uint_as_float(rs[g * 4 + e]), sc2, -lse)) : 0.f;
-            float dpe = __uint_as_float(rp[g * 4 + e]);
-            float pdrop = pe;
-            if (dc.thr) {
-              const bool keep = ((hsh >> (8 * e)) & 0xffu) >= dc.thr;
-              pdrop = keep ? pe * dc.scale : 0.f;
-              dpe = keep ? dpe * dc.scale : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              p[e] = ex2(fmaf(__uint_as_float(rs[g * 4 + e]), sc2, neglse));
+              if (tail && qt * 32 + g * 4 + e >= kvalid) p[e] = 0.f;
+              uint32_t dpb = rp[g * 4 + e];
+              if (dc.thr) dpb &= ~prmt(db, 0x8888u + 0x1111u * e);     // dropped element: dP = 0
+              ds[e] = p[e] * (__uint_as_float(dpb) - delta);            // x scale / (1 - p) at the dQ / dK flush
             }
-            p[e] = pdrop;
-            ds[e] = pe * (dpe - delta) * scale;
+            uint32_t w0 = pack2(p[0], p[1]), w1 = pack2(p[2], p[3]);
+            if (dc.thr) { w0 &= ~prmt(db, 0x9988u); w1 &= ~prmt(db, 0xbbaau); }   // kept probabilities (x 1/(1-p) at the dV flush)
+            pp[2 * g] = w0; pp[2 * g + 1] = w1;
+            pd[2 * g] = pack2(ds[0], ds[1]); pd[2 * g + 1] = pack2(ds[2], ds[3]);
           }
-          pp[2 * g] = pack2(p[0], p[1]); pp[2 * g + 1] = pack2(p[2], p[3]);
-          pd[2 * g] = pack2(ds[0], ds[1]); pd[2 * g + 1] = pack2(ds[2], ds[3]);
-        }
-        // the P / dS tiles are free once the MMA group of block n-1 has retired; flush that block on the way
-        if (n > 0) flush(n - 1);
+        };
+        if (kvalid == 128) body(false); else body(true);
+        // the P / dS tiles are free once the MMA group of block n-1 has retired
+        if (n > 0) { ptx::mbar_wait(acc_full, (n - 1) & 1); ptx::tc_fence_after(); }
         const uint32_t kb = (uint32_t)(qt >> 1) * kTile, c0 = (qt & 1) * 4;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -566,9 +622,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(pds_full);
+        if (n > 0) flush(n - 1);      // ... and that block's accumulators leave TMEM before the next group overwrites them
       }
     }
-    if (total > 0) flush(total - 1);
+    if (total > 0) {
+      ptx::mbar_wait(acc_full, (total - 1) & 1);
+      ptx::tc_fence_after();
+      flush(total - 1);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -628,11 +689,12 @@ int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int l
                      int lddo, const float *LSE, void *dQ, int lddq, void *dK, void *dV, int lddkv, int B, int H, int Lq,
                      int Lk, float scale, float drop_p, const unsigned long long *seed_ptr, unsigned int op_id,
                      cudaStream_t st) {
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, to;
   VPF_TRY(make_map3(&tq, Q, B, Lq, H, ldq));
   VPF_TRY(make_map3(&tk, K, B, Lk, H, ldkv));
   VPF_TRY(make_map3(&tv, V, B, Lk, H, ldkv));
   VPF_TRY(make_map3(&tdo, dO, B, Lq, H, lddo));
+  VPF_TRY(make_map3(&to, O, B, Lq, H, ldo));
   VPF_REQUIRE((lddq & 7) == 0 && (lddkv & 7) == 0 && (ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(dQ) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(dK) & 15) == 0 && (reinterpret_cast<uintptr_t>(dV) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(O) & 15) == 0, "attention_bwd (tcgen05): outputs must be 16-byte aligned, strides multiples of 8");
@@ -643,8 +705,8 @@ int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int l
   }
   const int items = B * H;
   const int grid = min(items, num_sms());
-  attn_tc_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, (const bf16 *)O, ldo, LSE, (bf16 *)dQ, lddq, (bf16 *)dK,
-                                                           (bf16 *)dV, lddkv, H, Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
+  attn_tc_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, to, LSE, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H,
+                                                           Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
   return check_launch("attn_tc_bwd_kernel");
 }
 
