@@ -41,7 +41,10 @@ def attn_ref(q, k, v, B, H, Lq, Lk, scale):
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk", [(3, 4, 128, 128), (2, 6, 144, 144), (2, 4, 96, 96), (2, 4, 128, 2048),
-                                       (1, 4, 128, 1000), (2, 2, 40, 75)])
+                                       (1, 4, 128, 1000), (2, 2, 40, 75),
+                                       # more (sample, head) items than persistent CTAs: several items per CTA, with one
+                                       # and with two query blocks, ragged key tails
+                                       (50, 4, 144, 144), (80, 4, 128, 300), (90, 4, 200, 130)])
 def test_attention_fwd_bwd(B, H, Lq, Lk):
     from vipformer_b200 import ops
 
@@ -70,7 +73,7 @@ def test_attention_dropout_consistency():
     must satisfy <dO, O(V)> == <dV, V>; and the keep rate must be 1-p."""
     from vipformer_b200 import ops
 
-    B, H, L = 2, 4, 128
+    B, H, L = 90, 4, 144        # two query blocks, two key blocks, several items per CTA
     D = H * 64
     seed = torch.tensor([77], device="cuda", dtype=torch.int64)
     q = rnd((B * L, D), 1, BF16)

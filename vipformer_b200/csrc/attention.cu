@@ -659,7 +659,7 @@ template <typename Kern> static int set_smem(Kern k, int bytes) {
   return VPF_OK;
 }
 
-// tcgen05 / TMEM path (attention_tc.cu): every attention with Lq <= 128 query tokens (the point-cloud branch)
+// tcgen05 / TMEM path (attention_tc.cu): every attention with Lq <= 256 query tokens (point-cloud AND image branch)
 namespace atc {
 int attention_tc_fwd(const void *Q, int ldq, const void *K, const void *V, int ldkv, void *O, int ldo, float *LSE, int B,
                      int H, int Lq, int Lk, float scale, float drop_p, const unsigned long long *seed_ptr,
@@ -669,9 +669,10 @@ int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int l
                      int Lk, float scale, float drop_p, const unsigned long long *seed_ptr, unsigned int op_id,
                      cudaStream_t st);
 }  // namespace atc
-static bool use_tc(int Lq) {
+static bool use_tc(int Lq, float drop_p) {
   static const int off = [] { const char *v = getenv("VPF_ATTN_TC"); return (v && v[0] == '0') ? 1 : 0; }();   // experiments: VPF_ATTN_TC=0
-  return !off && Lq <= 128;
+  // two query blocks at most (two dQ accumulators in TMEM); dropout threshold <= 128 / 256 (byte-parallel compare)
+  return !off && Lq <= 256 && drop_p <= 0.5f;
 }
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -689,7 +690,7 @@ int vpf_attention_fwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE(Lq >= 1 && Lk >= 1 && H >= 1 && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0, "attention_fwd: bad shape/stride");
   VPF_REQUIRE((long long)B * H <= 65535 * 1LL * 65535, "attention_fwd: too many heads");
   if (B == 0) return VPF_OK;
-  if (use_tc(Lq) && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O))
+  if (use_tc(Lq, drop_p) && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O))
     return atc::attention_tc_fwd(Q, ldq, K, V, ldkv, O, ldo, LSE, B, H, Lq, Lk, scale, drop_p, seed_ptr, op_id, (cudaStream_t)stream);
   if (Lq > 128 && Lq <= 160) {   // image branch (144 tokens): all queries in one 10-warp CTA, K/V streamed once
     const int smem = (160 + 4 * 64) * HD * 2;
@@ -719,7 +720,7 @@ int vpf_attention_bwd(const void *Q, int ldq, const void *K, const void *V, int 
   VPF_REQUIRE((ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddkv % 2) == 0, "attention_bwd: bad stride");
   if (B == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(Lq) && (lddq % 8) == 0 && (lddkv % 8) == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) &&
+  if (use_tc(Lq, drop_p) && (lddq % 8) == 0 && (lddkv % 8) == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) &&
       aligned16(dO) && aligned16(dQ) && aligned16(dK) && aligned16(dV))
     return atc::attention_tc_bwd(Q, ldq, K, V, ldkv, O, ldo, dO, lddo, LSE, dQ, lddq, dK, dV, lddkv, B, H, Lq, Lk, scale, drop_p,
                                  seed_ptr, op_id, st);

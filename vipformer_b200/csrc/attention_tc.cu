@@ -140,10 +140,22 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// rare path of the lazy running max: multiply this thread's 32 O columns (one TMEM lane) by corr.  Not inlined, so its
+// 32 registers do not add to the pressure of the softmax loop.
+__device__ __noinline__ void rescale_o(uint32_t taddr, float corr) {
+  uint32_t o[32];
+  ptx::tmem_ld_32x32(taddr, o);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * corr);
+  tmem_st32(taddr, o);
+  tmem_st_wait();
+}
+
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16 *__restrict__ O, int ldo, float *__restrict__ LSE,
-                   int H, int Lq, int Lk, int n_items, float scale, float drop_p,
+                   int H, int Lq, int Lk, int nqb, int n_items, float scale, float drop_p,
                    const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_s = ptx::smem_u32(smem);
@@ -181,11 +193,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------------------------------------------ TMA producer
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-      const int b = it / H, h = it - b * H;
+      const int bh = it / nqb, qb = it - bh * nqb, b = bh / H, h = bh - b * H;   // item = (sample, head, query block)
       mbar_wait_backoff(q_empty, (j & 1) ^ 1);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(q_full, kTile);
-        tma_load_3d(sQ, &tmQ, q_full, h * HD, 0, b);
+        tma_load_3d(sQ, &tmQ, q_full, h * HD, qb * 128, b);
       }
       __syncwarp();
       for (int t = 0; t < nkb; ++t, ++n) {
@@ -253,40 +265,57 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t kthr = 0x7f7f7f7fu + dc.thr * 0x01010101u;
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-      const int b = it / H, h = it - b * H;
-      const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
+      const int bh = it / nqb, qb = it - bh * nqb, b = bh / H, h = bh - b * H;
+      const int qrow = qb * 128 + row;                           // this thread's query token
+      const bool active = qb * 128 + quad * 32 < Lq;             // warp-uniform: any valid query row in this warp?
+      const uint32_t rowbase = ((uint32_t)bh * (uint32_t)Lq + (uint32_t)qrow) * kq4;
       float m = 0.f, l = 0.f;
       for (int t = 0; t < nkb; ++t, ++n) {
         const int kvalid = min(128, Lk - t * 128);
         const int j0 = hf * 64;                         // this thread's key offset inside the block
         ptx::mbar_wait(s_full, n & 1);
         ptx::tc_fence_after();
-        uint32_t s0[32], s1[32];
-        ptx::tmem_ld_32x32(t_row + j0, s0);
-        ptx::tmem_ld_32x32(t_row + j0 + 32, s1);
-        ptx::tmem_ld_wait();
-        // block maximum of this half (raw logits; sc2 > 0), exchanged with the other half as a bf16 UPPER bound
+        if (!active) {
+          // no valid query row in this warp (tail query block): keep the pipeline protocol, skip the arithmetic; the
+          // P rows stay whatever they were -- row m of P only reaches row m of O, which is never stored
+          named_bar(1 + quad, 64);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { ptx::mbar_arrive(s_empty); }
+          if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(p_full);
+          continue;
+        }
+        // block maximum of this half (raw logits; sc2 > 0).  Only 32 logits are kept in registers at a time: the upper
+        // 32 of this thread's 64 keys are read twice (maximum now, probabilities later) -- a tcgen05.ld is cheaper than
+        // the spills 64 live logits cost under the 96-register budget of two CTAs per SM.
+        uint32_t sx[32];
         float mx = -INFINITY;
+        ptx::tmem_ld_32x32(t_row + j0 + 32, sx);
+        ptx::tmem_ld_wait();
         if (kvalid == 128) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])));
+          for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sx[e]), __uint_as_float(sx[e + 1])));
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (j0 + e < kvalid) mx = fmaxf(mx, __uint_as_float(s0[e]));
-            if (j0 + 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(s1[e]));
-          }
+          for (int e = 0; e < 32; ++e) if (j0 + 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(sx[e]));
+        }
+        ptx::tmem_ld_32x32(t_row + j0, sx);
+        ptx::tmem_ld_wait();
+        if (kvalid == 128) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sx[e]), __uint_as_float(sx[e + 1])));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) if (j0 + e < kvalid) mx = fmaxf(mx, __uint_as_float(sx[e]));
         }
         mx *= sc2;
+        // exchanged with the other half of the row as a bf16 UPPER bound
         const float bound = mx + fabsf(mx) * 0.0078125f;          // >= mx after round-to-nearest to 8 mantissa bits
         xm[hf * 128 + row] = __float2bfloat16(mx == -INFINITY ? -1e30f : bound);
         named_bar(1 + quad, 64);
         const float m_blk = fmaxf(__bfloat162float(xm[row]), __bfloat162float(xm[128 + row]));
-        // S is in registers: the next block's logits may be issued.  (Arriving only AFTER the exchange read also orders
-        // the next block's xm writes -- which need the next s_full -- behind this block's xm reads.)
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(s_empty);
         bool need = t == 0 ? false : (m_blk > m + kLazy);
         if (t == 0) m = m_blk;
         if (__any_sync(0xffffffffu, need)) {
@@ -295,13 +324,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float corr = ex2(m - m_new);
           ptx::mbar_wait(pv_full, (n - 1) & 1);
           ptx::tc_fence_after();
-          uint32_t o[32];
-          ptx::tmem_ld_32x32(t_row + 128 + hf * 32, o);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * corr);
-          tmem_st32(t_row + 128 + hf * 32, o);
-          tmem_st_wait();
+          rescale_o(t_row + 128 + hf * 32, corr);
           l *= corr;
           m = m_new;
         }
@@ -330,8 +353,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             sts128(prow + tile_off(row, hh * 4 + c), w0, w1, w2, w3);
           }
         };
-        if (kvalid == 128) { half(s0, 0, false); half(s1, 1, false); }
-        else { half(s0, 0, true); half(s1, 1, true); }
+        if (kvalid == 128) half(sx, 0, false); else half(sx, 0, true);
+        ptx::tmem_ld_32x32(t_row + j0 + 32, sx);
+        ptx::tmem_ld_wait();
+        // S has been read for the last time: the next block's logits may be issued.  (This arrive comes after the xm
+        // exchange read above, which also orders the next block's xm writes -- they need the next s_full -- behind it.)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty);
+        if (kvalid == 128) half(sx, 1, false); else half(sx, 1, true);
         l += lsum;
         ptx::tc_fence_before();
         ptx::fence_proxy_async();
@@ -355,9 +385,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (hf == 0) { tot = l + *xl; *xl = tot; }
       named_bar(1 + quad, 64);
       if (hf == 1) tot = *xl;
-      if (row < Lq) {
+      if (qrow < Lq) {
         const float inv = dc.scale / tot;
-        bf16 *op = O + ((size_t)b * Lq + row) * ldo + h * HD + hf * 32;
+        bf16 *op = O + ((size_t)b * Lq + qrow) * ldo + h * HD + hf * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
@@ -367,7 +397,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           v.w = pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
           *reinterpret_cast<uint4 *>(op + 8 * c) = v;
         }
-        if (hf == 0) LSE[(size_t)it * Lq + row] = m + log2f(tot);
+        if (hf == 0) LSE[(size_t)bh * Lq + qrow] = m + log2f(tot);
       }
     }
   }
@@ -397,7 +427,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmO, const float *__restrict__ LSE, bf16 *__restrict__ dQ, int lddq,
-                   bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, int n_items,
+                   bf16 *__restrict__ dK, bf16 *__restrict__ dV, int lddkv, int H, int Lq, int Lk, int nqb, int n_items,
                    float scale, float drop_p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_s = ptx::smem_u32(smem);
@@ -431,31 +461,44 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sQdO = smem_s + kBOffQdO, sKV = smem_s + kBOffKV, sP = smem_s + kBOffP, sdS = smem_s + kBOffdS;
+  // One item = one (sample, head).  Its steps walk the key blocks (outer) and the query blocks (inner, nqb <= 2):
+  // dV / dK accumulate over the query blocks of a key block and are flushed after the last one; dQ of query block qb
+  // lives in its own TMEM columns (384 + 64 qb), accumulates over the key blocks and is flushed after the last one.
+  const int spi = nkb * nqb;   // steps per item
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total = my_items > 0 ? my_items * nkb : 0;
+  const int total = my_items > 0 ? my_items * spi : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    int n = 0, j = 0;
+    int j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-      const int b = it / H, h = it - b * H, qs = j & 1;
-      mbar_wait_backoff(&qdo_empty[qs], ((j >> 1) & 1) ^ 1);
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&qdo_full[qs], 3 * kTile);
-        tma_load_3d(sQdO + qs * 3 * kTile, &tmQ, &qdo_full[qs], h * HD, 0, b);
-        tma_load_3d(sQdO + qs * 3 * kTile + kTile, &tmdO, &qdo_full[qs], h * HD, 0, b);
-        tma_load_3d(sQdO + qs * 3 * kTile + 2 * kTile, &tmO, &qdo_full[qs], h * HD, 0, b);
-      }
-      __syncwarp();
-      for (int t = 0; t < nkb; ++t, ++n) {
-        const int st = n & 1;
-        mbar_wait_backoff(&kv_empty[st], ((n >> 1) & 1) ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
-          tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
-          tma_load_3d(sKV + st * 2 * kTile + kTile, &tmV, &kv_full[st], h * HD, t * 128, b);
+      const int b = it / H, h = it - b * H;
+      // loads are issued in the order the steps consume them (query block qb at its first key block, key block t at its
+      // first query block): the MMA warp looks one step ahead, so the first step of the next item must never wait behind
+      // a buffer that only the current item's LAST step releases
+      for (int u = 0; u < spi; ++u) {
+        const int t = u / nqb, qb = u - t * nqb;
+        if (t == 0) {
+          const int qi = j * nqb + qb, qs = qi & 1;
+          mbar_wait_backoff(&qdo_empty[qs], ((qi >> 1) & 1) ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&qdo_full[qs], 3 * kTile);
+            tma_load_3d(sQdO + qs * 3 * kTile, &tmQ, &qdo_full[qs], h * HD, qb * 128, b);
+            tma_load_3d(sQdO + qs * 3 * kTile + kTile, &tmdO, &qdo_full[qs], h * HD, qb * 128, b);
+            tma_load_3d(sQdO + qs * 3 * kTile + 2 * kTile, &tmO, &qdo_full[qs], h * HD, qb * 128, b);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        if (qb == 0) {
+          const int c = j * nkb + t, st = c & 1;
+          mbar_wait_backoff(&kv_empty[st], ((c >> 1) & 1) ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+            tma_load_3d(sKV + st * 2 * kTile, &tmK, &kv_full[st], h * HD, t * 128, b);
+            tma_load_3d(sKV + st * 2 * kTile + kTile, &tmV, &kv_full[st], h * HD, t * 128, b);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (warp == 1) {
@@ -463,10 +506,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t idesc_t = ptx::umma_idesc_bf16(128, 64, 1, 1);    // A = P / dS transposed (MN-major), B MN-major
     const uint32_t idesc_q = ptx::umma_idesc_bf16(128, 64, 0, 1);    // A = dS K-major, B = K MN-major
     auto issue_sdp = [&](int n) {
-      const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      const int j = n / spi, u = n - j * spi, t = u / nqb, qb = u - t * nqb;
+      const int qi = j * nqb + qb, qs = qi & 1, c = j * nkb + t, st = c & 1;
       const int kv16 = (min(128, Lk - t * 128) + 15) & ~15;
-      if (t == 0) ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
-      ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
+      if (t == 0) ptx::mbar_wait(&qdo_full[qs], (qi >> 1) & 1);
+      if (qb == 0) ptx::mbar_wait(&kv_full[st], (c >> 1) & 1);
       ptx::mbar_wait(sdp_empty, (n & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -481,7 +525,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (total > 0) issue_sdp(0);
     for (int n = 0; n < total; ++n) {
       if (n + 1 < total) issue_sdp(n + 1);
-      const int t = n % nkb, j = n / nkb, st = n & 1, qs = j & 1;
+      const int j = n / spi, u = n - j * spi, t = u / nqb, qb = u - t * nqb;
+      const int qi = j * nqb + qb, qs = qi & 1, c = j * nkb + t, st = c & 1;
       const int ksteps = (min(128, Lk - t * 128) + 15) >> 4;
       ptx::mbar_wait(pds_full, n & 1);
       ptx::mbar_wait(acc_empty, (n & 1) ^ 1);
@@ -494,19 +539,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t as = ptx::umma_smem_desc(sdS + k * 2048, kTile, 1024);
           const uint64_t bo = ptx::umma_smem_desc(do_s + k * 2048, kTile, 1024);
           const uint64_t bq = ptx::umma_smem_desc(q_s + k * 2048, kTile, 1024);
-          ptx::umma_bf16(tmem_base + 256, ap, bo, idesc_t, k > 0 ? 1u : 0u);   // dV = P^T dO
-          ptx::umma_bf16(tmem_base + 320, as, bq, idesc_t, k > 0 ? 1u : 0u);   // dK = dS^T Q
+          ptx::umma_bf16(tmem_base + 256, ap, bo, idesc_t, (qb > 0 || k > 0) ? 1u : 0u);   // dV += P^T dO
+          ptx::umma_bf16(tmem_base + 320, as, bq, idesc_t, (qb > 0 || k > 0) ? 1u : 0u);   // dK += dS^T Q
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // K = the block's keys: dS K-major k-block (k >> 2), K rows 16 k ..
           if (k < ksteps) {
             const uint64_t ad = ptx::umma_smem_desc(sdS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
             const uint64_t bk = ptx::umma_smem_desc(k_s + k * 2048, kTile, 1024);
-            ptx::umma_bf16(tmem_base + 384, ad, bk, idesc_q, (t > 0 || k > 0) ? 1u : 0u);   // dQ += dS K
+            ptx::umma_bf16(tmem_base + 384 + qb * 64, ad, bk, idesc_q, (t > 0 || k > 0) ? 1u : 0u);   // dQ[qb] += dS K
           }
         }
         ptx::umma_commit(acc_full);
-        ptx::umma_commit(&kv_empty[st]);
+        if (qb == nqb - 1) ptx::umma_commit(&kv_empty[st]);
         if (t == nkb - 1) ptx::umma_commit(&qdo_empty[qs]);
       }
       __syncwarp();
@@ -529,57 +574,79 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     };
     // flush of one finished block: dV, dK (rows = keys of that block) and, at the end of an item, dQ (rows = queries)
     auto flush = [&](int fn) {
-      const int ft = fn % nkb, fj = fn / nkb;
+      const int fj = fn / spi, fu = fn - fj * spi, ft = fu / nqb, fq = fu - ft * nqb;
       const int fit = (int)blockIdx.x + fj * (int)gridDim.x;
       const int fb = fit / H, fh = fit - fb * H;
+      const bool do_kv = fq == nqb - 1, do_q = ft == nkb - 1;      // warp-uniform
       uint32_t rv[16], rk[16], rq[16];
-      tmem_ld16(t_row + 256 + qt * 16, rv);
+      tmem_ld16(t_row + 256 + qt * 16, rv);      // (unconditional loads keep the three arrays in registers)
       tmem_ld16(t_row + 320 + qt * 16, rk);
-      const bool last = ft == nkb - 1;
-      if (last) tmem_ld16(t_row + 384 + qt * 16, rq);
+      tmem_ld16(t_row + 384 + fq * 64 + qt * 16, rq);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(acc_empty);
-      const int key = ft * 128 + row;
-      if (key < Lk) {
+      const int key = ft * 128 + row, qrow = fq * 128 + row;
+      if (do_kv && key < Lk) {
         uint4 *pk = reinterpret_cast<uint4 *>(dK + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16);
         uint4 *pv = reinterpret_cast<uint4 *>(dV + ((size_t)fb * Lk + key) * lddkv + fh * HD + qt * 16);
         pk[0] = pack8(rk, scale_d); pk[1] = pack8(rk + 8, scale_d);
         pv[0] = pack8(rv, dc.scale); pv[1] = pack8(rv + 8, dc.scale);
       }
-      if (last && row < Lq) {
-        uint4 *pq = reinterpret_cast<uint4 *>(dQ + ((size_t)fb * Lq + row) * lddq + fh * HD + qt * 16);
+      if (do_q && qrow < Lq) {
+        uint4 *pq = reinterpret_cast<uint4 *>(dQ + ((size_t)fb * Lq + qrow) * lddq + fh * HD + qt * 16);
         pq[0] = pack8(rq, scale_d); pq[1] = pack8(rq + 8, scale_d);
       }
     };
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-      const int qs = j & 1;
-      const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)row) * kq4;
-      // per-row constants of the item: lse (log2 units) and delta' = sum_d dO[i, d] O[i, d] / dropout scale
+      // per-row constants of the item's query blocks: lse (log2 units) and delta' = sum_d dO[i, d] O[i, d] / dropout scale
       float lse = INFINITY, delta = 0.f;     // rows >= Lq: p = exp2(-inf) = 0, dS = 0
-      if (row < Lq) lse = __ldg(LSE + (size_t)it * Lq + row);
-      ptx::mbar_wait(&qdo_full[qs], (j >> 1) & 1);
-      {
-        const uint32_t do_s = sQdO + qs * 3 * kTile + kTile, o_s = do_s + kTile;
+      for (int u = 0; u < spi; ++u, ++n) {
+        const int t = u / nqb, qb = u - t * nqb;
+        const int qi = j * nqb + qb, qs = qi & 1;
+        const int qrow = qb * 128 + row;
+        const uint32_t rowbase = ((uint32_t)it * (uint32_t)Lq + (uint32_t)qrow) * kq4;
+        if (t == 0 || nqb > 1) {     // (one query block: once per item; two: the blocks alternate, recompute per step)
+          lse = INFINITY; delta = 0.f;
+          if (qrow < Lq) lse = __ldg(LSE + (size_t)it * Lq + qrow);
+          if (t == 0) ptx::mbar_wait(&qdo_full[qs], (qi >> 1) & 1);
+          const uint32_t do_s = sQdO + qs * 3 * kTile + kTile, o_s = do_s + kTile;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a = lds128(o_s + tile_off(row, c)), d = lds128(do_s + tile_off(row, c));
-          const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a = lds128(o_s + tile_off(row, c)), d = lds128(do_s + tile_off(row, c));
+            const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a), *hd = reinterpret_cast<const __nv_bfloat162 *>(&d);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 fa = __bfloat1622float2(ha[q]), fd = __bfloat1622float2(hd[q]);
-            delta = fmaf(fa.x, fd.x, delta);
-            delta = fmaf(fa.y, fd.y, delta);
+            for (int q = 0; q < 4; ++q) {
+              const float2 fa = __bfloat1622float2(ha[q]), fd = __bfloat1622float2(hd[q]);
+              delta = fmaf(fa.x, fd.x, delta);
+              delta = fmaf(fa.y, fd.y, delta);
+            }
           }
+          delta *= inv_dscale;
         }
-        delta *= inv_dscale;
-      }
-      for (int t = 0; t < nkb; ++t, ++n) {
         const int kvalid = min(128, Lk - t * 128);
+        // warp-uniform: no valid query row in this warp (tail query block) or no valid key in this quarter (tail key block)
+        const bool dead = (qb * 128 + quad * 32 >= Lq) || (qt * 32 >= kvalid);
+        const uint32_t kb = (uint32_t)(qt >> 1) * kTile, c0 = (qt & 1) * 4;
         ptx::mbar_wait(sdp_full, n & 1);
         ptx::tc_fence_after();
+        if (dead) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(sdp_empty);
+          if (n > 0) { ptx::mbar_wait(acc_full, (n - 1) & 1); ptx::tc_fence_after(); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            sts128(sP + kb + tile_off(row, c0 + c), 0u, 0u, 0u, 0u);
+            sts128(sdS + kb + tile_off(row, c0 + c), 0u, 0u, 0u, 0u);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(pds_full);
+          if (n > 0) flush(n - 1);
+          continue;
+        }
         uint32_t rs[32], rp[32];
         ptx::tmem_ld_32x32(t_row + qt * 32, rs);
         ptx::tmem_ld_32x32(t_row + 128 + qt * 32, rp);
@@ -599,8 +666,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               p[e] = ex2(fmaf(__uint_as_float(rs[g * 4 + e]), sc2, neglse));
-              if (tail && qt * 32 + g * 4 + e >= kvalid) p[e] = 0.f;
               uint32_t dpb = rp[g * 4 + e];
+              if (tail && qt * 32 + g * 4 + e >= kvalid) { p[e] = 0.f; dpb = 0u; }   // (stale TMEM columns beyond the block's keys)
               if (dc.thr) dpb &= ~prmt(db, 0x8888u + 0x1111u * e);     // dropped element: dP = 0
               ds[e] = p[e] * (__uint_as_float(dpb) - delta);            // x scale / (1 - p) at the dQ / dK flush
             }
@@ -613,7 +680,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (kvalid == 128) body(false); else body(true);
         // the P / dS tiles are free once the MMA group of block n-1 has retired
         if (n > 0) { ptx::mbar_wait(acc_full, (n - 1) & 1); ptx::tc_fence_after(); }
-        const uint32_t kb = (uint32_t)(qt >> 1) * kTile, c0 = (qt & 1) * 4;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           sts128(sP + kb + tile_off(row, c0 + c), pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
@@ -679,9 +745,10 @@ int attention_tc_fwd(const void *Q, int ldq, const void *K, const void *V, int l
     VPF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     attr = true;
   }
-  const int items = B * H;
+  const int nqb = (Lq + 127) / 128;
+  const int items = B * H * nqb;
   const int grid = min(items, 2 * num_sms());
-  attn_tc_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, (bf16 *)O, ldo, LSE, H, Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
+  attn_tc_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, (bf16 *)O, ldo, LSE, H, Lq, Lk, nqb, items, scale, drop_p, seed_ptr, op_id);
   return check_launch("attn_tc_fwd_kernel");
 }
 
@@ -703,10 +770,11 @@ int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int l
     VPF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     attr = true;
   }
-  const int items = B * H;
+  const int items = B * H, nqb = (Lq + 127) / 128;
+  VPF_REQUIRE(nqb <= 2, "attention_bwd (tcgen05): at most 256 query tokens (two dQ accumulators in TMEM), got %d", Lq);
   const int grid = min(items, num_sms());
   attn_tc_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, to, LSE, (bf16 *)dQ, lddq, (bf16 *)dK, (bf16 *)dV, lddkv, H,
-                                                           Lq, Lk, items, scale, drop_p, seed_ptr, op_id);
+                                                           Lq, Lk, nqb, items, scale, drop_p, seed_ptr, op_id);
   return check_launch("attn_tc_bwd_kernel");
 }
 
