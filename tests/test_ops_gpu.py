@@ -93,6 +93,38 @@ def test_attention_dropout_consistency():
     assert abs(lhs - rhs) <= 2e-2 * abs(lhs) + 1e-2
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk", [(3, 4, 128, 128), (40, 4, 144, 144), (2, 4, 128, 300), (2, 2, 160, 40)])
+def test_attention_dropout_masks_equal_the_oracle_restatement(B, H, Lq, Lk):
+    """Dropout ON, exactly: the keep-mask the kernels regenerate from (seed, op id, element) is restated in
+    oracle/rng.py; softmax -> that mask -> . V in plain PyTorch must reproduce forward AND backward of both kernels
+    (tcgen05 path for Lq <= 256, one and two query blocks, ragged key tails; legacy mma.sync path beyond)."""
+    from oracle import rng as R
+    from vipformer_b200 import ops
+
+    D, scale, p, seed_v, op = H * 64, 64 ** -0.5, 0.1, 0x1234ABCD5678, 40
+    seed = torch.tensor([seed_v], device="cuda", dtype=torch.int64)
+    q = rnd((B * Lq, D), 1, BF16)
+    kv = rnd((B * Lk, 2 * D), 2, BF16)
+    k, v = kv[:, :D], kv[:, D:]
+    o, lse = ops.attention_fwd(q, k, v, B, H, Lq, Lk, scale, p, seed, op)
+    keep = torch.from_numpy(R.attention_keep(seed_v, op, p, B * H, Lq, Lk)).cuda().view(B, H, Lq, Lk)
+    assert 0.85 < (keep > 0).float().mean().item() < 0.95
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(B, Lq, H, 64).transpose(1, 2)
+    kh = kf.view(B, Lk, H, 64).transpose(1, 2)
+    vh = vf.view(B, Lk, H, 64).transpose(1, 2)
+    pr = (qh @ kh.transpose(-1, -2) * scale).softmax(-1) * keep
+    oref = (pr @ vh).transpose(1, 2).reshape(B * Lq, D)
+    assert relfro(o, oref) < 1e-2, relfro(o, oref)
+    do = rnd((B * Lq, D), 3, BF16)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    ops.attention_bwd(q, k, v, o, do, lse, dq, dkv[:, :D], dkv[:, D:], B, H, Lq, Lk, scale, p, seed, op)
+    oref.backward(do.float())
+    assert relfro(dq, qf.grad) < 2e-2 and relfro(dkv[:, :D], kf.grad) < 2e-2 and relfro(dkv[:, D:], vf.grad) < 2e-2, \
+        (relfro(dq, qf.grad), relfro(dkv[:, :D], kf.grad), relfro(dkv[:, D:], vf.grad))
+
+
 # --------------------------------------------------------------------------- layernorm
 @pytest.mark.parametrize("D", [64, 256, 384, 512, 768])
 def test_layernorm_fwd_bwd(D):
