@@ -176,12 +176,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def phase(msg):
+        if args.verbose and rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     # ---- warm-up (includes graph capture) + launch accounting
     _lib.launch_count_reset()
     load(0)
     eng.step()
     torch.cuda.synchronize()
     launches_capture = _lib.launch_count()
+    phase("first step (capture) done")
     launches_per_step = launches_capture // 3 if eng.graph is not None else launches_capture
     for i in range(max(args.warmup, 3)):
         load(i)
@@ -203,6 +208,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     loss_val = eng.losses.cpu().tolist()
+    phase(f"timed region done: {ms / args.steps:.2f} ms/step")
     # ---- e2e: pinned host -> device every step, loss read back every step
     for i in range(min(2, args.warmup)):      # untimed: creates the copy stream / staging buffers of the host path
         if args.e2e_sync:
@@ -232,6 +238,7 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
+    phase("e2e done")
     clocks = sampler.stop() if rank == 0 else None
 
     tms = torch.tensor([ms, max(ms_e2e, wall_e2e)], device=dev, dtype=torch.float64)
@@ -248,6 +255,7 @@ def run_ours(args):
     # roofline of the dominant kernel (tcgen05 GEMM): eager steps with CUDA events around every GEMM launch.  The step
     # contains collectives when world > 1, so EVERY rank runs it; rank 0 reports.
     roof = gemm_roofline(eng, load, pk, pk_kind)
+    phase("roofline pass done")
     barrier()
     if rank == 0:
         tok = tokenizer_rate(dev, pk)
@@ -275,11 +283,17 @@ def run_ours(args):
                              if world == 1 else "measured at N = 1 only"},
             "loss": loss_val,
         }
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        # tear-down order matters with NCCL kernels captured in a CUDA graph: drop the graph before the communicator
+        phase("teardown")
+        dist.barrier()
+        torch.cuda.synchronize()
+        eng.graph = None
+        del eng
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 def gemm_roofline(eng, load, pk, pk_kind):
@@ -367,6 +381,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-sync", action="store_true", help="e2e without input prefetch: H2D copy, step, D2H read in series")
     ap.add_argument("--no-overlap", action="store_true", help="run the image branch on the main stream (no two-stream overlap)")
+    ap.add_argument("--verbose", action="store_true", help="progress lines on stderr (rank 0)")
     ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also with world_size > 1 (default: eager there)")
     args = ap.parse_args()
     if args.impl == "reference":

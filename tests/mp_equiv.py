@@ -80,7 +80,13 @@ def main():
     assert torch.allclose(h0[0], h1[0], rtol=1e-3, atol=1e-3), (h0, h1)
     dist.barrier()
     if rank == 0:
-        print(f"MP_EQUIV_OK world={world} loss={mean_loss.cpu().tolist()} engine_losses={h0[-1].tolist()}")
+        print(f"MP_EQUIV_OK world={world} loss={mean_loss.cpu().tolist()} engine_losses={h0[-1].tolist()}", flush=True)
+    # tear-down: the CUDA graph holds captured NCCL kernels -- drop it (and the engines) before the communicator
+    torch.cuda.synchronize()
+    del eng, results
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
