@@ -23,9 +23,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CFG = dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, img=144, patch=12, seed=1)   # E1CL8SL-H4D256-L128-MR2
+# BASELINE.json configs[1] (the metric's configuration, default) and configs[2]; FLOPs: BASELINE.md section 2 (3 x forward)
+CFGS = {
+    "A": dict(name="E1CL8SL-H4D256-L128-MR2", flop=24.76e9, cfg=dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, img=144, patch=12, seed=1)),
+    "B": dict(name="E1CL8SL-H6D384-L128-MR4", flop=58.81e9, cfg=dict(D=384, H=6, n_sa=8, G=128, S=32, N=2048, MR=4, img=144, patch=12, seed=1)),
+}
+CFG = CFGS["A"]["cfg"]
 WORKLOAD = "pretrain step E1CL8SL-H4D256-L128-MR2: fwd (pc 2x + img) + NT-Xent (intra+cross) + bwd + grad all-reduce + AdamW"
-FLOP_PER_SHAPE_STEP = 24.76e9     # BASELINE.md section 2 (3 x forward matmul FLOPs)
+FLOP_PER_SHAPE_STEP = 24.76e9
+
+
+def select_config(key):
+    global CFG, WORKLOAD, FLOP_PER_SHAPE_STEP
+    c = CFGS[key]
+    CFG, FLOP_PER_SHAPE_STEP = c["cfg"], c["flop"]
+    WORKLOAD = f"pretrain step {c['name']}: fwd (pc 2x + img) + NT-Xent (intra+cross) + bwd + grad all-reduce + AdamW"
 
 
 def peaks():
@@ -114,6 +126,59 @@ def cpu_reference_step_rate(pairs, steps, warmup, threads=None):
     return pairs / (ms * 1e-3), ms, threads
 
 
+def gpu_eager_step_rate(pairs, steps, warmup, dev):
+    """The stronger comparator of SURVEY.md 8(d): the reference's math in STOCK PyTorch eager on the same B200 -- the
+    oracle port (oracle/model_ref.py + oracle/tokenizer_torch.py: the ATen op sequence the reference itself executes)
+    under bf16 autocast, cuBLAS / ATen kernels only, torch.optim.AdamW; same step, same batch, dropout off."""
+    import numpy as np
+    import torch
+
+    import _synth
+    from oracle import model_ref as M
+    from oracle import tokenizer_torch as TT
+
+    cfg = dict(CFG, b=pairs)
+    pc, im = _synth.build_models(cfg)
+    sd_pc = {k: v.clone().to(dev) for k, v in pc.state_dict().items()}
+    sd_im = {k: v.clone().to(dev) for k, v in im.state_dict().items()}
+    plist = []
+    for sd, model in ((sd_pc, pc), (sd_im, im)):
+        for k, _ in model.named_parameters():
+            sd[k] = sd[k].requires_grad_(True)
+            plist.append(sd[k])
+        for k in list(sd):
+            if "cross_attn_n." in k:
+                sd[k.replace("cross_attn_n.", "cross_attn_1.")] = sd[k]
+    del pc, im
+    opt = torch.optim.AdamW(plist, lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(7)
+    pts = torch.randn((2 * pairs, cfg["N"], 3), device=dev, generator=g)
+    pts = pts - pts.mean(1, keepdim=True)
+    pts = pts / pts.norm(dim=-1).amax(1).view(-1, 1, 1)
+    imgs = torch.randn((pairs, cfg["img"], cfg["img"], 3), device=dev, generator=g)
+    start = torch.randint(0, cfg["N"], (2 * pairs,), device=dev, generator=g)
+    tok = lambda p, G, S, st: TT.divide_patches(p, G, S, st, sorted_knn=False)
+    times = []
+    for it in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pf, _ = M.pc_forward(sd_pc, pts, start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, tokenizer=tok)
+            jf, _ = M.img_forward(sd_im, imgs, cfg["patch"], cfg["H"], cfg["n_sa"], True)
+        total, _, _ = M.pretrain_loss(pf.float(), jf.float())
+        total.backward()
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    del opt, plist, sd_pc, sd_im
+    torch.cuda.empty_cache()
+    return pairs / (ms * 1e-3), ms
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,7 +218,7 @@ def run_ours(args):
     cfg = dict(CFG, b=b)
     pc, im = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)     # script values (scripts/pretrain/*.sh)
     eng = PretrainEngine(pc, im, batch_pairs=b, num_points=cfg["N"], img_size=cfg["img"], lr=1e-3, seed=1,
-                         use_cuda_graph=(not args.no_graph) and (world == 1 or args.graph),
+                         use_cuda_graph=not args.no_graph,
                          overlap_branches=not args.no_overlap)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
 
@@ -254,23 +319,35 @@ def run_ours(args):
     pk, pk_kind = peaks()
     # roofline of the dominant kernel (tcgen05 GEMM): eager steps with CUDA events around every GEMM launch.  The step
     # contains collectives when world > 1, so EVERY rank runs it; rank 0 reports.
-    roof = gemm_roofline(eng, load, pk, pk_kind)
+    roof, launches_step = gemm_roofline(eng, load, pk, pk_kind, args)
     phase("roofline pass done")
     barrier()
     if rank == 0:
         tok = tokenizer_rate(dev, pk)
         # the CPU arm is timed on rank 0 at N = 1 only (it would only delay the other ranks' exit at N > 1)
         cpu_rate, cpu_ms, threads = cpu_reference_step_rate(16, 3, 1) if world == 1 else (None, None, None)
+        eager = None
+        if world == 1 and not args.no_eager_baseline:
+            torch.cuda.empty_cache()
+            try:
+                er, ems = gpu_eager_step_rate(b, 3, 2, dev)
+                eager = {"value": er, "unit": "shapes/s", "ms_per_step": ems, "ratio_ours_over_eager": value / er,
+                         "what": "oracle port (reference math, ATen/cuBLAS kernels) in stock PyTorch eager under bf16 autocast + "
+                                 "torch.optim.AdamW on this GPU, same config and pairs/step, dropout off, 3 steps after 2 warm-up"}
+            except Exception as ex:      # e.g. out of memory at a large --pairs: report, do not fail the bench line
+                eager = {"value": None, "error": f"{type(ex).__name__}: {str(ex)[:120]}"}
+        phase("baselines done")
         out = {
             "metric": "shapes/sec", "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": b, "global_pairs": b * world, "points": cfg["N"],
+            "config": {"workload": WORKLOAD, "config_key": args.config, "pairs_per_gpu": b, "global_pairs": b * world, "points": cfg["N"],
                        "parallelism": f"dp{world}", "negatives": "global (all-gather)" if eng.gather else "rank-local",
                        "two_stream_branches": eng.side is not None, "e2e_input": "synchronous" if args.e2e_sync else "H2D of step i+1 prefetched on a copy stream during step i; losses of step i read back (D2H) while step i+1 runs, the last before the clock stops", "cuda_graph": eng.graph is not None, "dropout": "atten 0.1 / mlp 0.5",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; 2 alternating input batches"},
             "e2e": {"value": e2e_value, "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches_per_step * args.steps * 2),
+            "gpu_launches": int(launches_step * args.steps),
+            "gpu_launches_per_step": int(launches_step),
             "clocks": clocks,
             "roofline": roof,
             "model_flops_fraction": {"flop_per_shape_step": FLOP_PER_SHAPE_STEP,
@@ -278,6 +355,7 @@ def run_ours(args):
                                      "peak_tflops": pk["bf16_tflops_sustained"], "peak_kind": pk_kind + " sustained",
                                      "frac": value / world * FLOP_PER_SHAPE_STEP / 1e12 / pk["bf16_tflops_sustained"]},
             "tokenizer": tok,
+            "gpu_eager_baseline": eager,
             "cpu_baseline": {"value": cpu_rate, "unit": "shapes/s", "cores": threads, "kind": "port",
                              "sample": "16 pairs/step x 3 steps (+1 warm-up) of the same workload, oracle port fp32, dropout off"
                              if world == 1 else "measured at N = 1 only"},
@@ -296,12 +374,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def gemm_roofline(eng, load, pk, pk_kind):
+def gemm_roofline(eng, load, pk, pk_kind, args):
     """Run steps eagerly with a CUDA-event pair around every tcgen05 GEMM launch (same stream): achieved TFLOP/s =
-    algorithmic FLOPs (2*M*N*K of each launch) / summed launch durations."""
+    algorithmic FLOPs (2*M*N*K of each launch) / summed launch durations.  Also counts the kernels this library
+    launches in one step (vpf_launch_count), and the algorithmic bytes of the GEMM launches (operands + result once)."""
     import torch
 
-    from vipformer_b200 import ops
+    from vipformer_b200 import _lib, ops
 
     rec = []
     orig = ops.gemm
@@ -311,35 +390,52 @@ def gemm_roofline(eng, load, pk, pk_kind):
         M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
         K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
         N = kw.get("N") or (b_.shape[1] if b_mn else b_.shape[0])
+        obytes = 0 if out is None else M * N * out.element_size() * (2 if kw.get("mode", 0) == 1 else 1)   # residual: read + write
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = orig(a, b_, out, **kw)
         e1.record()
-        rec.append((e0, e1, 2.0 * M * N * K))
+        rec.append((e0, e1, 2.0 * M * N * K, 2.0 * (M * K + N * K) + obytes))
         return r
 
     ops.gemm = timed_gemm
     side, eng.side = eng.side, None     # serial schedule: a launch timed while the other branch runs is not its own time
+    launches = 0
     try:
         for i in range(2):
             rec.clear()
             load(i)
+            torch.cuda.synchronize()
+            c0 = _lib.launch_count()
             eng._step_body()
             torch.cuda.synchronize()
+            launches = _lib.launch_count() - c0
     finally:
         ops.gemm = orig
         eng.side = side
-    t = sum(e0.elapsed_time(e1) for e0, e1, _ in rec) * 1e-3
-    fl = sum(f for _, _, f in rec)
+    t = sum(e0.elapsed_time(e1) for e0, e1, _, _ in rec) * 1e-3
+    fl = sum(f for _, _, f, _ in rec)
+    ab = sum(b for _, _, _, b in rec)
     ach = fl / t / 1e12
     peak = pk["bf16_tflops_sustained"]
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 254 GEMM launches of one step at
-    # 256 pairs/GPU: profiles/r01_step_launches_v6.csv (ncu, one capture: 27.3 GB read + 6.8 GB written); algorithmic = operands + result
-    traffic = 134.0e6 if eng.b == 256 else None
-    return {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA)", "bound": "tensor", "achieved": ach, "peak": peak,
-            "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "peak_kind": pk_kind + " sustained (kernel timed inside a long step)",
+    # measured DRAM traffic of the GEMM launches: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu
+    # launch list of `tools/profile_step.py` committed under profiles/ (tools/dram_summary.py writes the JSON); only
+    # quoted when it was taken on the configuration being benchmarked
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "r02_step_dram.json")
+    if os.path.exists(tj):
+        d = json.load(open(tj))
+        if d.get("pairs") == eng.b and d.get("config") == args.config:
+            traffic = d["gemm"]["bytes_per_launch"]
+            traffic_src = f"profiles/r02_step_dram.json (ncu, git {d.get('git', '?')}, {d['gemm']['launches']} launches)"
+    roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA)", "bound": "tensor", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "traffic_source": traffic_src, "algorithmic_bytes": ab / max(1, len(rec)),
+            "algorithmic_bytes_unit": "bytes/launch (operands + result once; residual read)",
+            "peak_kind": pk_kind + " sustained (kernel timed inside a long step)",
             "launches_per_step": len(rec), "avg_launch_us": 1e6 * t / max(1, len(rec)), "gemm_ms_per_step": 1e3 * t,
             "gemm_flops_per_step": fl}
+    return roof, launches
 
 
 def tokenizer_rate(dev, pk):
@@ -377,13 +473,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU (weak scaling)")
+    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU (weak scaling); the reference's own per-rank batch is 55")
+    ap.add_argument("--config", default="A", choices=sorted(CFGS), help="A = E1CL8SL-H4D256-L128-MR2 (the metric's config), B = E1CL8SL-H6D384-L128-MR4")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-PyTorch-eager comparator leg (N = 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-sync", action="store_true", help="e2e without input prefetch: H2D copy, step, D2H read in series")
     ap.add_argument("--no-overlap", action="store_true", help="run the image branch on the main stream (no two-stream overlap)")
     ap.add_argument("--verbose", action="store_true", help="progress lines on stderr (rank 0)")
-    ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also with world_size > 1 (default: eager there)")
+    ap.add_argument("--graph", action="store_true", help="(kept for compatibility: CUDA-graph replay is the default at every world size)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         run_reference(args)
     else:

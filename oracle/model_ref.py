@@ -230,12 +230,16 @@ def latent_head(sd, k, x, training, running_out=None):
     return F.linear(x, sd[k + ".5.weight"])
 
 
-def pc_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=None):
-    """CrossFormer_pc_mp.forward, partseg.py:527-550, with the tokenizer pinned as in oracle/tokenizer_oracle.c."""
+def pc_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=None, tokenizer=None):
+    """CrossFormer_pc_mp.forward, partseg.py:527-550, with the tokenizer pinned as in oracle/tokenizer_oracle.c
+    (`tokenizer`: alternative callable (pts, G, S, start_idx) -> (neighbors, centers), e.g. oracle.tokenizer_torch on a GPU)."""
     with _prefix("pc."):
         pts_embs = input_adapter(sd, "input_adapter", pts)
-        nb, ce = T.divide_patches(pts.detach().numpy(), G, S, np.asarray(start_idx))
-        nb, ce = torch.from_numpy(nb).to(pts.dtype), torch.from_numpy(ce).to(pts.dtype)
+        if tokenizer is not None:
+            nb, ce = tokenizer(pts.detach(), G, S, start_idx)
+        else:
+            nb, ce = T.divide_patches(pts.detach().numpy(), G, S, np.asarray(start_idx))
+            nb, ce = torch.from_numpy(nb).to(pts.dtype), torch.from_numpy(ce).to(pts.dtype)
         group_embs = group2emb(sd, "group2emb", nb, training, running_out)
         pos_embs = position_emb(sd, "position_emb", ce)
         x = encoder(sd, "encoder", group_embs, pos_embs, pts_embs, H, n_sa)
@@ -266,8 +270,8 @@ def ntxent(out0, out1, temperature=0.1):
     b = out0.shape[0]
     z = torch.cat([out0, out1], 0)
     logits = torch.einsum("nc,mc->nm", z, z) / temperature
-    logits = logits[~torch.eye(2 * b, dtype=torch.bool)].view(2 * b, -1)
-    labels = torch.cat([torch.arange(b) + b - 1, torch.arange(b)])
+    logits = logits[~torch.eye(2 * b, dtype=torch.bool, device=z.device)].view(2 * b, -1)
+    labels = torch.cat([torch.arange(b, device=z.device) + b - 1, torch.arange(b, device=z.device)])
     return F.cross_entropy(logits, labels)
 
 

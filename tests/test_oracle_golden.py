@@ -51,3 +51,23 @@ def test_fps_properties():
         assert sorted(fi[b].tolist()) == list(range(256))
     with pytest.raises(RuntimeError):
         T.farthest_point_sample(pts, 4, np.array([0, 0, 256], dtype=np.int64))
+
+
+def test_torch_tokenizer_restatement_matches_c_oracle():
+    """oracle/tokenizer_torch.py (the reference's ATen op sequence, used by bench.py's GPU-eager comparator) against the C
+    oracle on generic clouds: FPS indices exact, neighbour SETS equal, centres exact; order equal where distances are untied."""
+    import numpy as np
+    import torch
+
+    import _synth
+    from oracle import tokenizer as T
+    from oracle import tokenizer_torch as TT
+
+    pts = _synth.make_clouds("randn", 3, 1024, 5)
+    start = _synth.make_start(3, 1024, 5)
+    nb, ce, fi, ki = T.divide_patches(pts, 96, 32, start, return_indices=True)
+    tnb, tce = TT.divide_patches(torch.from_numpy(pts), 96, 32, torch.from_numpy(start))
+    assert np.array_equal(tce.numpy(), ce)
+    assert np.array_equal(TT.farthest_point_sample(torch.from_numpy(pts), 96, torch.from_numpy(start)).numpy(), fi)
+    same = (tnb.numpy() == nb).all(-1)
+    assert same.mean() > 0.999       # identical up to fp32 ties between the expanded-form bmm and the pinned C arithmetic
