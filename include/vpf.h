@@ -226,6 +226,10 @@ int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float
  * with nchw=1 which folds the permute of pretrain.py:179, -> bf16 rows). */
 int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, int nchw, void *stream);
 int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream);
+/* out[i] = x[i] * s[0], s a DEVICE scalar (upstream gradient of a scalar loss). */
+int vpf_scale_by(const float *x, const float *s, float *out, long long n, void *stream);
+/* dst[r, c] = alpha * src[r, c] over a [rows, cols] window of two row-strided fp32 arrays (padded head buffers). */
+int vpf_copy2d(const float *src, int lds, float *dst, int ldd, long long rows, int cols, float alpha, void *stream);
 
 /* ------------------------------------------------------------------ loss + optimiser
  * NT-Xent (lightly 1.1.21 NTXentLoss; call sites pretrain.py:155,196,202). */
@@ -243,6 +247,11 @@ int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc,
                    int n_c, int D, int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base,
                    float temperature, float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx,
                    void *stream);
+/* nn.CrossEntropyLoss(label_smoothing = eps), mean reduction -- the fine-tune objective (ft_cls.py:145,176).
+ * logits fp32 [n, ld] (C valid columns), labels int64 [n]; loss_out (+=, zero it first) and dlogits fp32 [n, ldd]
+ * = d(mean loss)/d(logits), both produced in one pass. */
+int vpf_ce_ls(const float *logits, int ld, const long long *labels, int n, int C, float eps, float *loss_out,
+              float *dlogits, int ldd, void *stream);
 /* torch.optim.AdamW step (pretrain.py:121-124,210) on a flat buffer, refreshing the bf16 shadow. */
 int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n,
               const float *lr_ptr, float beta1, float beta2, float eps, float weight_decay,

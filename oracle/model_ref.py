@@ -247,6 +247,38 @@ def pc_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=Non
         return latent_head(sd, "latent_head", backbone, training, running_out), backbone
 
 
+def finetune_head(sd, k, x, training, running_out=None):
+    """partseg.py:573-582 on backbone feats [B,2D]: 3 x {BatchNorm1d, ReLU, Linear (with bias)}."""
+    for i, (bn, fc) in enumerate(((0, 2), (3, 5), (6, 8))):
+        x = _relu(_bn(sd, f"{k}.{bn}", x, training, running_out), f"cls.relu{i + 1}")
+        x = F.linear(x, sd[f"{k}.{fc}.weight"], sd[f"{k}.{fc}.bias"])
+    return x
+
+
+def pc_ft_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=None, tokenizer=None):
+    """CrossFormer_pc_mp_ft.forward, partseg.py:584-605 -> logits [B, num_obj_classes]."""
+    with _prefix("pc."):
+        pts_embs = input_adapter(sd, "input_adapter", pts)
+        if tokenizer is not None:
+            nb, ce = tokenizer(pts.detach(), G, S, start_idx)
+        else:
+            nb, ce = T.divide_patches(pts.detach().numpy(), G, S, np.asarray(start_idx))
+            nb, ce = torch.from_numpy(nb).to(pts.dtype), torch.from_numpy(ce).to(pts.dtype)
+        group_embs = group2emb(sd, "group2emb", nb, training, running_out)
+        pos_embs = position_emb(sd, "position_emb", ce)
+        x = encoder(sd, "encoder", group_embs, pos_embs, pts_embs, H, n_sa)
+        backbone = torch.cat([_max1(x, "pool.max"), x.mean(1)], 1)
+        return finetune_head(sd, "finetune_head", backbone, training, running_out)
+
+
+def cross_entropy_ls(logits, labels, eps=0.2):
+    """torch.nn.CrossEntropyLoss(label_smoothing=eps), ft_cls.py:145 -- written out (mean reduction)."""
+    logp = F.log_softmax(logits, dim=1)
+    nll = -logp.gather(1, labels.view(-1, 1)).squeeze(1)
+    smooth = -logp.mean(1)
+    return ((1 - eps) * nll + eps * smooth).mean()
+
+
 def patch2emb(sd, k, imgs, patch):
     """partseg.py:631-634: Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)' + Linear."""
     B, Hh, Ww, C = imgs.shape

@@ -84,6 +84,40 @@ def build_models(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
     return pc, im
 
 
+FT_CASES = {
+    # fine-tune classification fixtures (BASELINE configs[3]: ScanObjectNN-shaped, 15 classes)
+    "ft_small": dict(D=128, H=2, n_sa=2, G=32, S=8, N=128, MR=2, b=10, classes=15, seed=61),
+    "ft_cfgA": dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, b=8, classes=15, seed=62),
+}
+
+
+def build_ft_model(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
+    """CrossFormer_pc_mp_ft with the kwargs of the reference's utils.build_ft_cls (utils.py:203-224)."""
+    import importlib
+
+    import torch
+
+    pcmod = importlib.import_module(pkg + ".model.pointcloud")
+    part = importlib.import_module(pkg + ".model.pointcloud.partseg")
+    torch.manual_seed(cfg["seed"])
+    ad = pcmod.PointCloudInputAdapter(pointcloud_shape=(cfg["N"], 3), num_input_channels=cfg["D"])
+    return part.CrossFormer_pc_mp_ft(input_adapter=ad, num_latents=cfg["G"], num_latent_channels=cfg["D"], group_size=cfg["S"],
+                                     num_cross_attention_layers=1, num_cross_attention_heads=cfg["H"],
+                                     num_self_attention_layers=cfg["n_sa"], num_self_attention_heads=cfg["H"],
+                                     mlp_widen_factor=cfg["MR"], max_dpr=0.0, atten_drop=atten_drop, mlp_drop=mlp_drop,
+                                     modal_prior=True, num_obj_classes=cfg["classes"])
+
+
+def ft_inputs(cfg):
+    import torch
+
+    pts = make_clouds("randn", cfg["b"], cfg["N"], cfg["seed"] + 1)
+    start = make_start(cfg["b"], cfg["N"], cfg["seed"])
+    g = torch.Generator().manual_seed(cfg["seed"] + 3)
+    labels = torch.randint(0, cfg["classes"], (cfg["b"],), generator=g)
+    return torch.from_numpy(pts), start, labels
+
+
 def perturb_state_dict(sd, seed):
     """Deterministic perturbation so LayerNorm/BatchNorm affine terms and biases are not at their trivial init."""
     import torch

@@ -83,11 +83,69 @@ def run_case(name, cfg):
     print("model", name, "loss", out["loss"], "pc_feats", out["pc_feats"].shape)
 
 
+def run_ft_case(name, cfg):
+    """CrossFormer_pc_mp_ft + CrossEntropyLoss(label_smoothing=0.2) (partseg.py:553-605, ft_cls.py:145,176) from the REAL
+    reference: logits, loss, per-parameter gradient norms, a few full gradients, updated running statistics."""
+    _refshim.load()
+    import vipformer.model.pointcloud.utils as U
+
+    ref = _synth.build_ft_model(cfg, pkg="vipformer")
+    mine = _synth.build_ft_model(cfg, pkg="vipformer_b200")
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys()), "fine-tune state_dict keys differ from the reference"
+    for k in rs:
+        assert rs[k].shape == ms[k].shape and torch.equal(rs[k], ms[k]), f"state_dict value differs at {k}"
+    sd = _synth.perturb_state_dict(ref.state_dict(), cfg["seed"] + 10)
+    ref.load_state_dict(sd)
+    ref.train()
+    pts, start, labels = _synth.ft_inputs(cfg)
+
+    class _T:
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+    proxy = _T()
+    proxy.randint = _PinnedRandint(start)
+    orig_torch, orig_knn = U.torch, U.knn_point
+
+    def knn_sorted(nsample, xyz, new_xyz):
+        d = U.square_distance(new_xyz, xyz)
+        return torch.topk(d, nsample, dim=-1, largest=False, sorted=True)[1]
+
+    # partseg.py imported divide_patches by name: patch the functions it resolves at call time (module globals of utils)
+    try:
+        U.torch, U.knn_point = proxy, knn_sorted
+        logits = ref(pts)
+    finally:
+        U.torch, U.knn_point = orig_torch, orig_knn
+    loss = torch.nn.CrossEntropyLoss(label_smoothing=0.2)(logits, labels)
+    loss.backward()
+    out = dict(logits=logits.detach().numpy(), loss=np.array([loss.item()]))
+    names, norms = [], []
+    for k, p in ref.named_parameters():
+        if p.grad is None:        # latent_head: unused by the fine-tune forward (find_unused_parameters=True, ft_cls.py:86)
+            continue
+        names.append(k)
+        norms.append(p.grad.double().norm().item())
+        if k in FULL_GRADS or k.startswith("finetune_head.8") or k == "finetune_head.2.weight":
+            out[f"grad::{k}"] = p.grad.numpy()
+    out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms)
+    for k, v in ref.state_dict().items():
+        if "running_" in k:
+            out[f"buf::{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, f"model_{name}.npz"), **out)
+    print("ft model", name, "loss", out["loss"], "logits", out["logits"].shape, "params with grad", len(names))
+
+
 def main(what):
     torch.set_num_threads(8)
-    for name, cfg in _synth.MODEL_CASES.items():
-        run_case(name, cfg)
+    if "model" in what:
+        for name, cfg in _synth.MODEL_CASES.items():
+            run_case(name, cfg)
+    if "ft" in what:
+        for name, cfg in _synth.FT_CASES.items():
+            run_ft_case(name, cfg)
 
 
 if __name__ == "__main__":
-    main(["model"])
+    main(sys.argv[1:] or ["model", "ft"])

@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import _synth
 from oracle import model_ref as M
@@ -94,3 +95,55 @@ def test_ntxent_restatement_equals_closed_form():
         a = M.ntxent(x0.double(), x1.double()).item()
         c = M.ntxent_closed_form(x0.double(), x1.double()).item()
         assert abs(a - c) < 1e-9
+
+
+def oracle_ft_run(cfg, pins=None, dtype=torch.float32):
+    """Fine-tune oracle run shared with the GPU tests: mirror init -> perturbed state_dict -> oracle forward, label-smoothed
+    CE (eps 0.2, ft_cls.py:145), backward."""
+    model = _synth.build_ft_model(cfg)
+    sd = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(model.state_dict(), cfg["seed"] + 10).items()}
+    names = [k for k, _ in model.named_parameters()]
+    for k in names:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    for k in list(sd.keys()):
+        if ".cross_attn_n." in k:
+            sd[k.replace(".cross_attn_n.", ".cross_attn_1.")] = sd[k]
+    pts, start, labels = _synth.ft_inputs(cfg)
+    run = {}
+    with M.choices(pins) as ch:
+        logits = M.pc_ft_forward(sd, pts.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], True, run)
+        loss = M.cross_entropy_ls(logits, labels, 0.2)
+        loss.backward()
+    return dict(sd=sd, names=names, logits=logits.detach(), loss=loss.item(), run=run, rec=ch.rec, inputs=(pts, start, labels))
+
+
+@pytest.mark.parametrize("name", ["ft_small", "ft_cfgA"])
+def test_finetune_oracle_matches_reference(name, golden_dir):
+    """CrossFormer_pc_mp_ft + CrossEntropyLoss(label_smoothing=0.2): oracle restatement vs vectors from the REAL reference."""
+    cfg = _synth.FT_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    torch.set_num_threads(8)
+    o = oracle_ft_run(cfg)
+    assert _rel(o["logits"], g["logits"]) < 1e-4
+    assert abs(o["loss"] - float(g["loss"][0])) < 1e-4
+    assert abs(F.cross_entropy(o["logits"], o["inputs"][2], label_smoothing=0.2).item() - o["loss"]) < 1e-5
+    gnames = list(g["grad_names"])
+    norms = {k: o["sd"][k].grad.double().norm().item() for k in gnames}
+    ref = dict(zip(gnames, g["grad_norms"]))
+    mx = max(ref.values())
+    for k in gnames:
+        assert abs(norms[k] - ref[k]) <= 2e-3 * ref[k] + 1e-5 * mx, k
+    # the pre-training projection head is unused by the fine-tune forward: no gradient in the reference, zero here
+    for k in o["names"]:
+        if k.startswith("latent_head"):
+            assert k not in gnames and (o["sd"][k].grad is None or o["sd"][k].grad.abs().max() == 0)
+    for key in g.files:
+        if key.startswith("grad::"):
+            k = key.split("::")[1]
+            assert _rel(o["sd"][k].grad, g[key]) < 2e-3 or np.abs(g[key]).max() < 1e-5 * mx, k
+        if key.startswith("buf::"):
+            k = key.split("::")[1]
+            if k.startswith("latent_head"):      # unused head: running statistics stay at their (perturbed) initial values
+                assert np.array_equal(g[key], o["sd"][k].numpy()), k
+            else:
+                assert _rel(o["run"][k], g[key]) < 1e-4, k

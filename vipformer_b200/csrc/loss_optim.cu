@@ -151,6 +151,36 @@ l2norm_bwd_kernel(const float *__restrict__ G, const float *__restrict__ z, cons
   for (int d = lane; d < D; d += 32) dx[(size_t)k * D + d] = (G[(size_t)k * D + d] * s - z[(size_t)k * D + d] * zg) * inv;
 }
 
+// nn.CrossEntropyLoss(label_smoothing = eps), mean reduction (ft_cls.py:145,176): one warp per sample.
+//   loss_i = (1 - eps) * (-log p_i[y_i]) + eps / C * sum_c (-log p_i[c]);   dlogits_i = (p_i - ((1 - eps) onehot(y_i) + eps / C)) / n
+// forward and the logit gradient in one pass (the gradient is scaled by the upstream scalar in the autograd backward).
+__global__ void __launch_bounds__(256)
+ce_ls_kernel(const float *__restrict__ logits, int ld, const long long *__restrict__ labels, int n, int C, float eps,
+             float *__restrict__ loss_out, float *__restrict__ dlogits, int ldd) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float *row = logits + (size_t)i * ld;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float se = 0.f, sx = 0.f;
+  for (int c = lane; c < C; c += 32) { se += __expf(row[c] - m); sx += row[c]; }
+  se = wsum(se);
+  sx = wsum(sx);
+  const float lse = m + __logf(se);
+  const int y = (int)labels[i];
+  const float inv_n = 1.f / (float)n, u = eps / (float)C;
+  for (int c = lane; c < C; c += 32) {
+    const float p = __expf(row[c] - lse);
+    dlogits[(size_t)i * ldd + c] = (p - ((c == y ? 1.f - eps : 0.f) + u)) * inv_n;
+  }
+  if (lane == 0) {
+    const float nll = lse - row[y], smooth = lse - sx / (float)C;
+    atomicAdd(loss_out, ((1.f - eps) * nll + eps * smooth) * inv_n);
+  }
+}
+
 // fused AdamW (torch.optim.AdamW semantics) over a flat parameter buffer; refreshes the bf16 shadow.
 // state[0] = step count (int64, already advanced for this step), lr read from device memory.
 __global__ void __launch_bounds__(256)
@@ -230,6 +260,14 @@ int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc,
   VPF_TRY(check_launch("sgemm_kernel"));
   l2norm_bwd_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(G_ws, zr, norm, gscale / temperature, upstream, dx, n_r, D);
   return check_launch("l2norm_bwd_kernel");
+}
+
+int vpf_ce_ls(const float *logits, int ld, const long long *labels, int n, int C, float eps, float *loss_out,
+              float *dlogits, int ldd, void *stream) {
+  VPF_REQUIRE(logits && labels && loss_out && dlogits && C >= 1 && ld >= C && ldd >= C && eps >= 0.f && eps < 1.f, "ce_ls: bad arguments");
+  if (n == 0) return VPF_OK;
+  ce_ls_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, n, C, eps, loss_out, dlogits, ldd);
+  return check_launch("ce_ls_kernel");
 }
 
 int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, long long n, const float *lr_ptr,

@@ -539,6 +539,21 @@ __global__ void add_scale_kernel(const float *__restrict__ a, const float *__res
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = alpha * (a[i] + (b ? b[i] : 0.f));
 }
 
+// dst[r, c] = alpha * src[r, c] over a [rows, cols] window of two row-strided fp32 arrays
+__global__ void copy2d_kernel(const float *__restrict__ src, int lds, float *__restrict__ dst, int ldd, long long rows, int cols, float alpha) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const size_t r = i / cols, c = i - r * cols;
+    dst[r * ldd + c] = alpha * src[r * lds + c];
+  }
+}
+
+// out[i] = x[i] * s[0]  (s on the device: an upstream scalar gradient)
+__global__ void scale_by_kernel(const float *__restrict__ x, const float *__restrict__ s, float *__restrict__ out, size_t n) {
+  const float f = s[0];
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = x[i] * f;
+}
+
 static inline int grid_for(size_t total) { return (int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)); }
 static inline int rows_per_cta_for(long long R) { return (int)max((long long)64, ceil_div(R, (long long)num_sms() * 8)); }
 
@@ -667,6 +682,20 @@ int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, 
   }
   patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (bf16 *)out_bf16, H, W, Ci, P, nchw, total);
   return check_launch("patchify_kernel");
+}
+
+int vpf_scale_by(const float *x, const float *s, float *out, long long n, void *stream) {
+  VPF_REQUIRE(x && s && out, "scale_by: null pointer");
+  if (n == 0) return VPF_OK;
+  scale_by_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, s, out, (size_t)n);
+  return check_launch("scale_by_kernel");
+}
+
+int vpf_copy2d(const float *src, int lds, float *dst, int ldd, long long rows, int cols, float alpha, void *stream) {
+  VPF_REQUIRE(src && dst && lds >= cols && ldd >= cols, "copy2d: bad arguments");
+  if (rows == 0 || cols == 0) return VPF_OK;
+  copy2d_kernel<<<grid_for((size_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols, alpha);
+  return check_launch("copy2d_kernel");
 }
 
 int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream) {

@@ -259,33 +259,82 @@ def patch2emb_bwd(de, c, G):
     _wgrad(g, c.P, G.w)
 
 
-# ===================================================== pooling + latent_head (partseg.py:519-525,547-548)
+# ===================================================== pooling + BN/ReLU/Linear heads
+# latent_head (partseg.py:519-525: 2 x {BN1d, ReLU, Linear no bias}) and finetune_head (partseg.py:573-582: 3 x {BN1d, ReLU,
+# Linear with bias}) are the same chain; a stage is NS(bn_w, bn_b, rm, rv, w (bf16 shadow [Cout, Cin]), b (fp32 or None)).
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def mlp_head_fwd(x, stages, training, save=True):
+    """x fp32 [B, C0] -> fp32 [B, Cout_last] (a view of a buffer whose row stride is padded to 8 columns)."""
+    B = x.shape[0]
+    ctxs = []
+    for st in stages:
+        a, bst = ops.bn_forward(x, st.bn_w, st.bn_b, st.rm, st.rv, training, True)
+        cout = st.w.shape[0]
+        ybuf = _empty((B, _pad8(cout)), F32, x)
+        y = ybuf[:, :cout]
+        ops.gemm(a, st.w, y, bias=st.b)
+        if save:
+            ctxs.append(NS(x=x, a=a, st=bst))
+        x = y
+    return x, ctxs
+
+
+def mlp_head_bwd(dy, ctxs, stages, grads):
+    """dy fp32 [B, Cout_last] -> fp32 [B, C0]; parameter gradients accumulate into grads[i] = NS(bn_w, bn_b, w, b)."""
+    B = dy.shape[0]
+    g = None
+    for i in range(len(stages) - 1, -1, -1):
+        st, G, c = stages[i], grads[i], ctxs[i]
+        cout, cin = st.w.shape
+        if g is None:     # fp32 upstream of the last Linear -> bf16 GEMM operand in a buffer with 16-byte aligned rows
+            gp = ops.zeros_(_empty((B, _pad8(cout)), F32, dy)) if cout % 8 else _empty((B, cout), F32, dy)
+            ops.copy2d(dy, gp[:, :cout])
+            gfull = ops.dropout_grad(gp, 0.0, None, 0)
+            g = gfull[:, :cout]
+        if G.b is not None:
+            if cout % 8 == 0:
+                ops.colsum(g, sum32=G.b)
+            else:       # padded operand buffer: column sums of the padded width, then the valid part into the bias gradient
+                tmp = ops.zeros_(_empty((_pad8(cout),), F32, dy))
+                ops.colsum(gfull, sum32=tmp)
+                ops.add_scale(tmp[:cout], G.b, 1.0, out=G.b)
+        _wgrad(g, c.a, G.w)
+        da = _empty((B, cin), BF16, dy)
+        _dgrad(g, st.w, da)
+        g = ops.bn_backward(da, c.x, c.st, True, G.bn_w, G.bn_b, out_dtype=F32 if i == 0 else BF16)
+    return g
+
+
 def pool_head_fwd(x, W, bn, B, L, D, training, save=True):
     """x fp32 [B*L, D] -> (feats fp32 [B, D], backbone fp32 [B, 2D])."""
     pooled, am = ops.token_pool_fwd(x, B, L, D)
-    a1, st1 = ops.bn_forward(pooled, W.bn1_w, W.bn1_b, bn.rm1, bn.rv1, training, True)
-    y2 = _empty((B, D), F32, x)
-    ops.gemm(a1, W.wa, y2)
-    a2, st2 = ops.bn_forward(y2, W.bn2_w, W.bn2_b, bn.rm2, bn.rv2, training, True)
-    feats = _empty((B, D), F32, x)
-    ops.gemm(a2, W.wb, feats)
-    ctx = NS(pooled=pooled, am=am, a1=a1, st1=st1, y2=y2, a2=a2, st2=st2) if save else None
+    stages = [NS(bn_w=W.bn1_w, bn_b=W.bn1_b, rm=bn.rm1, rv=bn.rv1, w=W.wa, b=None),
+              NS(bn_w=W.bn2_w, bn_b=W.bn2_b, rm=bn.rm2, rv=bn.rv2, w=W.wb, b=None)]
+    feats, cs = mlp_head_fwd(pooled, stages, training, save)
+    ctx = NS(pooled=pooled, am=am, a1=cs[0].a, a2=cs[1].a, cs=cs, stages=stages) if save else None
     return feats, pooled, ctx
 
 
 def pool_head_bwd(dfeats, dbackbone, c, W, G, B, L, D):
     if dfeats is not None:
-        g = ops.dropout_grad(dfeats, 0.0, None, 0)
-        _wgrad(g, c.a2, G.wb)
-        da2 = _empty((B, D), BF16, g)
-        _dgrad(g, W.wb, da2)
-        dy2 = ops.bn_backward(da2, c.y2, c.st2, True, G.bn2_w, G.bn2_b, out_dtype=BF16)
-        _wgrad(dy2, c.a1, G.wa)
-        da1 = _empty((B, 2 * D), BF16, g)
-        _dgrad(dy2, W.wa, da1)
-        dpooled = ops.bn_backward(da1, c.pooled, c.st1, True, G.bn1_w, G.bn1_b, out_dtype=F32)
+        grads = [NS(bn_w=G.bn1_w, bn_b=G.bn1_b, w=G.wa, b=None), NS(bn_w=G.bn2_w, bn_b=G.bn2_b, w=G.wb, b=None)]
+        dpooled = mlp_head_bwd(dfeats, c.cs, c.stages, grads)
         if dbackbone is not None:
             dpooled = ops.add_scale(dpooled, dbackbone.contiguous(), 1.0)
     else:
         dpooled = dbackbone.contiguous()
     return ops.token_pool_bwd(dpooled, c.am, B, L, D)
+
+
+def pool_cls_head_fwd(x, stages, B, L, D, training, save=True):
+    """Fine-tune classifier (partseg.py:597-604): x fp32 [B*L, D] -> logits fp32 [B, classes]."""
+    pooled, am = ops.token_pool_fwd(x, B, L, D)
+    logits, cs = mlp_head_fwd(pooled, stages, training, save)
+    return logits, (NS(am=am, cs=cs, a=[c.a for c in cs]) if save else None)
+
+
+def pool_cls_head_bwd(dlogits, c, stages, grads, B, L, D):
+    return ops.token_pool_bwd(mlp_head_bwd(dlogits, c.cs, stages, grads), c.am, B, L, D)

@@ -135,6 +135,39 @@ class NTXentLoss(nn.Module):
         return _NTXentFn.apply(out0, out1, float(self.temperature), bool(self.gather_distributed))
 
 
+class _CELabelSmoothingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, eps):
+        _lib.require_cuda(logits, labels)
+        if logits.dim() != 2:
+            raise ValueError("CrossEntropyLoss expects [batch, classes] logits")
+        x = logits if (logits.dtype == F32 and logits.stride(1) == 1) else logits.float().contiguous()
+        loss, d = ops.ce_label_smoothing(x, labels.reshape(-1).long(), eps)
+        ctx.d = d
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d = ctx.d
+        up = dloss.float().reshape(1)
+        out = torch.empty_like(d)
+        _lib.call("vpf_scale_by", ops._p(d), ops._p(up), ops._p(out), ops._ll(d.numel()), ops._s())
+        return out, None, None
+
+
+class CrossEntropyLoss(nn.Module):
+    """`torch.nn.CrossEntropyLoss(label_smoothing=eps)` (mean reduction) as used by ft_cls.py:145,176."""
+
+    def __init__(self, label_smoothing: float = 0.0):
+        super().__init__()
+        if not 0.0 <= label_smoothing < 1.0:
+            raise ValueError("label_smoothing must be in [0, 1)")
+        self.label_smoothing = float(label_smoothing)
+
+    def forward(self, input, target):
+        return _CELabelSmoothingFn.apply(input, target, self.label_smoothing)
+
+
 class _PretrainLossFn(torch.autograd.Function):
     """total = NTXent(t1, t2) + w * NTXent((t1+t2)/2, img)   (pretrain.py:189-207, modality 'both')."""
 

@@ -502,6 +502,80 @@ class CrossFormer_pc_mp(nn.Module):
         return x_latent_feats, backbone_feats
 
 
+class _FinetuneHead(nn.Sequential):
+    """finetune_head of partseg.py:573-582: 3 x {BatchNorm1d, ReLU, Linear (with bias)}, fused with the max/mean token
+    pooling of partseg.py:601.  forward(x_latent [B,L,D]) -> logits [B, num_obj_classes]."""
+
+    def _stages(self, grads=False):
+        out = []
+        for bn_i, fc_i in ((0, 2), (3, 5), (6, 8)):
+            bn, fc = self[bn_i], self[fc_i]
+            if grads:
+                out.append(NS(bn_w=bn.weight.grad, bn_b=bn.bias.grad, w=fc.weight.grad, b=fc.bias.grad))
+            else:
+                out.append(NS(bn_w=bn.weight, bn_b=bn.bias, rm=bn.running_mean, rv=bn.running_var,
+                              w=params.wb(fc.weight), b=fc.bias))
+        return out
+
+    def forward(self, x_latent):
+        return _PoolClsHeadFn.apply(x_latent, _anchor(self), self)
+
+
+class _PoolClsHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, mod):
+        _lib.require_cuda(x)
+        arena = _root_prepare(mod, x.device)
+        B, L, D = x.shape
+        stages = mod._stages()
+        save = any(ctx.needs_input_grad)
+        logits, c = Fn.pool_cls_head_fwd(_as_f32_2d(x, D), stages, B, L, D, mod.training, save)
+        _rt.tap("cls_head", c)
+        if mod.training:
+            _bump(mod[0]); _bump(mod[3]); _bump(mod[6])
+        if save:
+            ctx.c, ctx.mod, ctx.arena, ctx.stages, ctx.shape = c, mod, arena, stages, (B, L, D)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.arena.ensure_grads()
+        B, L, D = ctx.shape
+        dx = Fn.pool_cls_head_bwd(dlogits.float(), ctx.c, ctx.stages, ctx.mod._stages(grads=True), B, L, D)
+        ctx.c = None
+        return dx.view(B, L, D), None, None
+
+
+class CrossFormer_pc_mp_ft(CrossFormer_pc_mp):
+    """partseg.py:553-605: the pre-trained point-cloud branch + a 3-stage classification head; forward(pts [B,N,3]) ->
+    logits [B, num_obj_classes].  `latent_head` stays in the module (and in the state_dict) unused, exactly as in the
+    reference, so pre-training checkpoints load with strict=False and only `finetune_head.*` is missing (ft_cls.py:92-98)."""
+
+    def __init__(self, input_adapter=None, num_latents=128, num_latent_channels=384, group_size=32,
+                 num_cross_attention_layers=1, num_cross_attention_heads=6, num_self_attention_layers=6,
+                 num_self_attention_heads=6, mlp_widen_factor=4, max_dpr=0, atten_drop=0.1, mlp_drop=0.5,
+                 modal_prior=True, num_obj_classes=40):
+        super().__init__(input_adapter, num_latents, num_latent_channels, group_size, num_cross_attention_layers,
+                         num_cross_attention_heads, num_self_attention_layers, num_self_attention_heads,
+                         mlp_widen_factor, max_dpr, atten_drop, mlp_drop, modal_prior)
+        D = num_latent_channels
+        self.finetune_head = _FinetuneHead(nn.BatchNorm1d(2 * D), nn.ReLU(), nn.Linear(2 * D, D), nn.BatchNorm1d(D), nn.ReLU(),
+                                           nn.Linear(D, D // 2), nn.BatchNorm1d(D // 2), nn.ReLU(),
+                                           nn.Linear(D // 2, num_obj_classes))
+
+    def forward(self, pts):
+        return self.finetune_head(self._tokens(pts))
+
+
+def load_pretrained(model, state_dict):
+    """ft_cls.py:92-98 without the DDP wrapper: load a pre-training checkpoint of CrossFormer_pc_mp into a fine-tune model
+    (`strict=False`: `finetune_head.*` stays at its initialisation).  Keys saved from a DDP-wrapped model ("module.") are
+    accepted.  Returns the (missing, unexpected) key lists of load_state_dict."""
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+    res = model.load_state_dict(sd, strict=False)
+    return list(res.missing_keys), list(res.unexpected_keys)
+
+
 class CrossFormer_img_mp(nn.Module):
     """partseg.py:608-680.  forward(imgs [B,H,W,3] NHWC) -> (feats [B,D], backbone [B,2D])."""
 

@@ -115,6 +115,24 @@ def add_scale(a, b, alpha, out=None):
     return out
 
 
+def copy2d(src, dst, alpha=1.0):
+    """dst[:, :] = alpha * src over equal [rows, cols] windows of row-strided fp32 tensors."""
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1 and src.dtype == F32 and dst.dtype == F32
+    _lib.call("vpf_copy2d", _p(src), _i(src.stride(0)), _p(dst), _i(dst.stride(0)), _ll(rows), _i(cols), _f(alpha), _s())
+    return dst
+
+
+def ce_label_smoothing(logits, labels, eps):
+    """-> (loss fp32 [1], dlogits fp32 [n, C] = d loss / d logits).  logits fp32 [n, C] (row-strided view allowed)."""
+    n, C = logits.shape
+    assert logits.dtype == F32 and logits.stride(1) == 1 and labels.dtype == torch.int64 and labels.numel() == n
+    loss = zeros_(torch.empty(1, dtype=F32, device=logits.device))
+    d = torch.empty((n, C), dtype=F32, device=logits.device)
+    _lib.call("vpf_ce_ls", _p(logits), _i(logits.stride(0)), _p(labels.contiguous()), _i(n), _i(C), _f(eps), _p(loss), _p(d), _i(C), _s())
+    return loss, d
+
+
 # ----------------------------------------------------------------------------- attention
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, drop_p=0.0, seed=None, op_id=0):
     """q: [B*Lq, >=H*64] view (row stride = q.stride(0)); k, v: views of one buffer with the same row stride."""
