@@ -226,6 +226,10 @@ int vpf_linear3_bn_bwd(const void *dh_bf16, const float *p, int ldp, const float
  * with nchw=1 which folds the permute of pretrain.py:179, -> bf16 rows). */
 int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, int P, int nchw, void *stream);
 int vpf_add_scale(const float *a, const float *b, float *out, float alpha, long long n, void *stream);
+/* Inference: fold an eval-mode BatchNorm1d (scale, shift from vpf_bn_finalize with training = 0) into the 1x1
+ * convolution / Linear in front of it: Wout = bf16(scale[n] * W[n, :]), bout = scale * b + shift (utils.py:161-163). */
+int vpf_bn_fold(const float *W, const float *b, const float *scale, const float *shift, void *Wout_bf16, float *bout,
+                int N, int K, void *stream);
 /* out[i] = x[i] * s[0], s a DEVICE scalar (upstream gradient of a scalar loss). */
 int vpf_scale_by(const float *x, const float *s, float *out, long long n, void *stream);
 /* dst[r, c] = alpha * src[r, c] over a [rows, cols] window of two row-strided fp32 arrays (padded head buffers). */

@@ -244,3 +244,32 @@ def test_config_B_full_depth_matches_oracle():
     bad, worst = compare_grads(r, o, 8e-2)      # same gate as the linear case above (measured 6.3e-2)
     print(f"[cfgB] worst per-parameter rel-Frobenius gradient error with pinned choices: {worst:.4f}")
     assert not bad, bad
+
+
+def test_feature_extractor_matches_eval_forward_and_oracle():
+    """vipformer_b200.inference.FeatureExtractor (CUDA-graph replay, BN folded, device-resident result, ragged tail)
+    == model(data)[1] in eval mode == the oracle's eval-mode backbone features (pretrain.py:228-276)."""
+    from oracle import model_ref as M
+    from vipformer_b200.inference import FeatureExtractor
+
+    cfg = dict(_synth.MODEL_CASES["cfgA"], N=1024, b=2, seed=43)
+    o0 = oracle_run(cfg)
+    pc, _ = _synth.build_models(cfg, atten_drop=0.1, mlp_drop=0.5)
+    pc.load_state_dict({k: v.detach() for k, v in o0["sd_pc"].items() if k in pc.state_dict()})
+    n, B = 21, 8
+    pts = torch.from_numpy(_synth.make_clouds("randn", n, 1024, 77))
+    start = torch.from_numpy(_synth.make_start(B, 1024, 77))
+    outs = []
+    for graph in (True, False):
+        fx = FeatureExtractor(pc, B, 1024, use_cuda_graph=graph)
+        fx.fixed_start = start.cuda()
+        outs.append(fx(pts.pin_memory()))
+    assert outs[0].shape == (n, 2 * cfg["D"]) and torch.equal(outs[0], outs[1])
+    sd = {k: v.detach() for k, v in o0["sd_pc"].items()}
+    with torch.no_grad():
+        for i0 in range(0, n, B):
+            m = min(B, n - i0)
+            _, rb = M.pc_forward(sd, pts[i0:i0 + m], start[:m].numpy(), cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"], training=False)
+            assert relfro(outs[0][i0:i0 + m], rb) < 2e-2, (i0, relfro(outs[0][i0:i0 + m], rb))
+    f, l = FeatureExtractor(pc, B, 1024).extract([(pts[:8], torch.arange(8)), (pts[8:13], torch.arange(5))])
+    assert f.shape == (13, 2 * cfg["D"]) and l.tolist() == list(range(8)) + list(range(5)) and np.isfinite(f).all()

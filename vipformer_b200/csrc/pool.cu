@@ -554,6 +554,18 @@ __global__ void scale_by_kernel(const float *__restrict__ x, const float *__rest
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = x[i] * f;
 }
 
+// eval-mode BatchNorm folded into the preceding 1x1 convolution (inference): Wout[n, k] = bf16(scale[n] * W[n, k]),
+// bout[n] = scale[n] * b[n] + shift[n]
+__global__ void bn_fold_kernel(const float *__restrict__ W, const float *__restrict__ b, const float *__restrict__ scale,
+                               const float *__restrict__ shift, __nv_bfloat16 *__restrict__ Wout, float *__restrict__ bout, int N, int K) {
+  const size_t n = (size_t)N * K;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const int r = (int)(i / K);
+    Wout[i] = __float2bfloat16(W[i] * scale[r]);
+    if (i - (size_t)r * K == 0) bout[r] = (b ? b[r] : 0.f) * scale[r] + shift[r];
+  }
+}
+
 static inline int grid_for(size_t total) { return (int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)); }
 static inline int rows_per_cta_for(long long R) { return (int)max((long long)64, ceil_div(R, (long long)num_sms() * 8)); }
 
@@ -682,6 +694,14 @@ int vpf_patchify(const float *img, void *out_bf16, int B, int H, int W, int Ci, 
   }
   patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (bf16 *)out_bf16, H, W, Ci, P, nchw, total);
   return check_launch("patchify_kernel");
+}
+
+int vpf_bn_fold(const float *W, const float *b, const float *scale, const float *shift, void *Wout_bf16, float *bout, int N,
+                int K, void *stream) {
+  VPF_REQUIRE(W && scale && shift && Wout_bf16 && bout, "bn_fold: null pointer");
+  if (N == 0 || K == 0) return VPF_OK;
+  bn_fold_kernel<<<grid_for((size_t)N * K), 256, 0, (cudaStream_t)stream>>>(W, b, scale, shift, (__nv_bfloat16 *)Wout_bf16, bout, N, K);
+  return check_launch("bn_fold_kernel");
 }
 
 int vpf_scale_by(const float *x, const float *s, float *out, long long n, void *stream) {

@@ -158,10 +158,20 @@ def group2emb_fwd(nb, W, bn, cfg, training, save=True):
     ops.gemm(h1, W.w2, f2, bias=W.b2, gm_S=S, gm_bf16=gmax, gm_argmax=am2)
     # conv3 on cat([global, local]) split into a per-group and a per-point half (saves 1/4 of the block's FLOPs)
     u = _empty((Gt, 256), F32, nb)
-    ops.gemm(gmax, W.w3[:, :128], u, bias=W.b3)
-    y3 = _empty((R, 256), BF16, nb)
-    ops.gemm(f2, W.w3[:, 128:], y3, rg_bias=u, rg_shift=int(math.log2(S)))
-    h3, st3 = ops.bn_forward(y3, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, training, True)
+    if not training:
+        # inference: the eval-mode BatchNorm (running statistics) is folded into conv3 -- scaled weight rows, folded bias,
+        # ReLU in the GEMM epilogue -- so neither y3 nor a separate normalisation pass exists (utils.py:161-163)
+        st3 = ops.bn_stats_finalize(None, R, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, False)
+        w3s, b3s = ops.bn_fold(W.w3_f32, W.b3, st3.scale, st3.shift)
+        ops.gemm(gmax, w3s[:, :128], u, bias=b3s)
+        h3 = _empty((R, 256), BF16, nb)
+        ops.gemm(f2, w3s[:, 128:], h3, rg_bias=u, rg_shift=int(math.log2(S)), act=ACT_RELU)
+        y3 = None
+    else:
+        ops.gemm(gmax, W.w3[:, :128], u, bias=W.b3)
+        y3 = _empty((R, 256), BF16, nb)
+        ops.gemm(f2, W.w3[:, 128:], y3, rg_bias=u, rg_shift=int(math.log2(S)))
+        h3, st3 = ops.bn_forward(y3, W.bn3_w, W.bn3_b, bn.rm3, bn.rv3, training, True)
     # conv4 + max over the patch (utils.py:187-188): pooled from the fp32 accumulators in the GEMM epilogue, the [R, D]
     # pre-pool tensor is never stored.  (The transposed, register-only variant `gm_cols=True` measured slower: 864 vs 600 us.)
     tok = _empty((Gt, D), F32, nb)

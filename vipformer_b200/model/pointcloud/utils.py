@@ -159,7 +159,7 @@ class Group2Emb(nn.Module):
         f, s = self.first_conv, self.second_conv
         wb = _params.wb
         return _NS(w1=f[0].weight.view(64, 3), b1=f[0].bias, bn1_w=f[1].weight, bn1_b=f[1].bias,
-                   w2=wb(f[3].weight).view(128, 64), b2=f[3].bias, w3=wb(s[0].weight).view(256, 256), b3=s[0].bias,
+                   w2=wb(f[3].weight).view(128, 64), b2=f[3].bias, w3=wb(s[0].weight).view(256, 256), w3_f32=s[0].weight.view(256, 256), b3=s[0].bias,
                    bn3_w=s[1].weight, bn3_b=s[1].bias, w4=wb(s[3].weight).view(self.dim_model, 256), b4=s[3].bias)
 
     def _grads(self):

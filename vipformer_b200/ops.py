@@ -115,6 +115,15 @@ def add_scale(a, b, alpha, out=None):
     return out
 
 
+def bn_fold(W, b, scale, shift):
+    """-> (bf16 [N, K] = scale[:, None] * W, fp32 [N] = scale * b + shift): eval-mode BatchNorm folded into its Linear."""
+    N, K = W.shape
+    Wo = torch.empty((N, K), dtype=BF16, device=W.device)
+    bo = torch.empty(N, dtype=F32, device=W.device)
+    _lib.call("vpf_bn_fold", _p(W.contiguous()), _p(b), _p(scale), _p(shift), _p(Wo), _p(bo), _i(N), _i(K), _s())
+    return Wo, bo
+
+
 def copy2d(src, dst, alpha=1.0):
     """dst[:, :] = alpha * src over equal [rows, cols] windows of row-strided fp32 tensors."""
     rows, cols = src.shape
