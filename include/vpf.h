@@ -90,6 +90,13 @@ int vpf_divide_patches_host(const float *pts_host, int B, int N, int C, int G,
                             void *stream);
 
 
+/* Device-side augmentation: the trans_1 / trans_2 chain of datasets/data.py:16-36 (data_utils.py:56-221) on a batch of
+ * clouds, in front of the tokenizer.  pts / out [B,N,3] fp32; params [B,6] = (scale, rotation angle about y, three
+ * translation fractions of the bounding box, drop ratio); jitter [B,N,3] = N(0, std) draws before the clamp to
+ * +-jitter_clip; drop_u [B,N] uniform draws (point i is overwritten by point 0 when drop_u <= drop ratio). */
+int vpf_augment_clouds(const float *pts, const float *params, const float *jitter, const float *drop_u, float *out,
+                       int B, int N, float jitter_clip, void *stream);
+
 /* ------------------------------------------------------------ dense contraction
  * One tcgen05/TMA GEMM serves every Linear / 1x1-Conv1d on the path, forward and
  * backward (vipformer/model/pointcloud/partseg.py:46-49,191-198 Linear layers;

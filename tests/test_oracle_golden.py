@@ -71,3 +71,14 @@ def test_torch_tokenizer_restatement_matches_c_oracle():
     assert np.array_equal(TT.farthest_point_sample(torch.from_numpy(pts), 96, torch.from_numpy(start)).numpy(), fi)
     same = (tnb.numpy() == nb).all(-1)
     assert same.mean() > 0.999       # identical up to fp32 ties between the expanded-form bmm and the pinned C arithmetic
+
+
+def test_augment_oracle_matches_reference_golden(golden_dir):
+    """oracle/augment.py against vectors from the reference's own data_utils classes (tests/make_golden_aug.py)."""
+    import numpy as np
+
+    from oracle import augment as A
+
+    g = np.load(os.path.join(golden_dir, "aug_trans1.npz"))
+    out = A.augment_batch(g["raw"], {k: g[k] for k in ("scaler", "angle", "trans", "jitter", "drop_ratio", "drop_u")})
+    assert np.abs(out - g["out"]).max() < 2e-6
