@@ -48,9 +48,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the hint
+// expires) instead of spinning through try_wait / branch pairs that compete for issue slots with the working warps
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef VPF_MBAR_SPIN
   while (!mbar_try_wait(bar, parity)) {
   }
+#else
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
+#endif
 }
 
 // ---- TMA (cp.async.bulk.tensor) ------------------------------------------------

@@ -55,7 +55,7 @@ def _mlp_bwd(dx2, c, W, G, T, D, p_drop, seed, op_id):
     _dgrad(g2, W.w2, dh)
     dz = ops.gelu_bwd(dh, c.z, colsum=G.b1)
     _wgrad(dz, c.xn2, G.w1)
-    dxn2 = _empty((T, D), F32, dx2)
+    dxn2 = _empty((T, D), BF16, dx2)      # gradient w.r.t. the LayerNorm output: a bf16 operand like dh / dz / dqkv
     _dgrad(dz, W.w1, dxn2)
     return ops.layernorm_bwd(dxn2, c.x1, c.mean2, c.rstd2, W.ln2_w, dres=dx2, dgamma=G.ln2_w, dbeta=G.ln2_b)
 
@@ -89,7 +89,7 @@ def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos):
     ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], c.o, do, c.lse, dqkv[:, :D], dqkv[:, D:2 * D],
                       dqkv[:, 2 * D:], B, H, L, L, cfg.scale, cfg.p_attn, seed, op_base)
     _wgrad(dqkv, c.xn, G.wqkv)
-    dxn = _empty((T, D), F32, dx2)
+    dxn = _empty((T, D), BF16, dx2)
     _dgrad(dqkv, W.wqkv, dxn)
     return ops.layernorm_bwd(dxn, c.xin, c.mean1, c.rstd1, W.ln1_w, dres=dx1, dgamma=G.ln1_w, dbeta=G.ln1_b, dpos=dpos)
 
@@ -127,7 +127,7 @@ def ca_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, need_dkv=True):
     ops.attention_bwd(c.q, c.kvp[:, :D], c.kvp[:, D:], c.o, do, c.lse, dq, dkvp[:, :D], dkvp[:, D:], B, H, L, Lk,
                       cfg.scale, cfg.p_attn, seed, op_base)
     _wgrad(dq, c.qn, G.wq)
-    dqn = _empty((T, D), F32, dx2)
+    dqn = _empty((T, D), BF16, dx2)
     _dgrad(dq, W.wq, dqn)
     dxq = ops.layernorm_bwd(dqn, c.xin, c.meanq, c.rstdq, W.qn_w, dres=dx1, dgamma=G.qn_w, dbeta=G.qn_b, dpos=dpos)
     _wgrad(dkvp, c.kvn, G.wkv)
