@@ -218,6 +218,88 @@ __device__ __forceinline__ bool knn_select_twopass(const float4 *s_pt, int N, in
   return true;
 }
 
+// Register-blocked two-pass selection: one warp handles QB queries at once, so every point is read from shared memory
+// ONCE per pass for QB distance evaluations.  (One query per warp was shared-memory-bandwidth bound: 2 x 16 B per
+// (query, point) pair = 8.4 MB per cloud through a 128 B/clk port.)  Same arithmetic, thresholds, candidate order and
+// rank rule as knn_select_twopass, per query.  ok[q] = false when that query's candidate list overflowed.
+template <int QB>
+__device__ __forceinline__ void knn_select_twopass_multi(const float4 *s_pt, int N, int nsample, const float (&cx)[QB],
+                                                         const float (&cy)[QB], const float (&cz)[QB], const float (&c2)[QB],
+                                                         int lane, unsigned long long *cand /*[QB][kKnnCap]*/,
+                                                         uint32_t *sel /*[QB][32]*/, uint32_t (&Llo)[QB], bool (&ok)[QB]) {
+  const float inf = __int_as_float(0x7f800000);
+  float m1[QB], m2[QB], tau[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) m1[q] = m2[q] = inf;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    if (i < N) {
+      const float4 P = s_pt[i];
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        const float d = knn_dist(P, cx[q], cy[q], cz[q], c2[q]);
+        const float t = fmaxf(m1[q], d);
+        m1[q] = fminf(m1[q], d);
+        m2[q] = fminf(m2[q], t);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    const float a = warp_sort_asc(m1[q], lane), bs = warp_sort_asc(m2[q], lane);
+    const float lo32 = fminf(a, __shfl_sync(kFull, bs, 31 - lane));
+    tau[q] = ord2f(__reduce_max_sync(kFull, f2ord(lo32)));
+  }
+  int cnt[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) cnt[q] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < N;
+    const float4 P = s_pt[valid ? i : 0];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      const float d = knn_dist(P, cx[q], cy[q], cz[q], c2[q]);
+      const bool pred = valid && d <= tau[q];
+      const unsigned mask = __ballot_sync(kFull, pred);
+      if (mask) {
+        if (pred) {
+          const int pos = cnt[q] + __popc(mask & lt);
+          if (pos < kKnnCap) cand[q * kKnnCap + pos] = ((unsigned long long)f2ord(d) << 32) | (uint32_t)i;
+        }
+        cnt[q] += __popc(mask);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    ok[q] = cnt[q] <= kKnnCap;     // warp-uniform
+    if (!ok[q]) continue;
+    const unsigned long long *cq = cand + q * kKnnCap;
+    uint32_t *sq = sel + q * 32;
+    for (int j0 = 0; j0 < cnt[q]; j0 += 64) {
+      const int ja = j0 + lane, jb = j0 + 32 + lane;
+      const unsigned long long ca = ja < cnt[q] ? cq[ja] : ~0ull, cb = jb < cnt[q] ? cq[jb] : ~0ull;
+      int ra = 0, rb = 0;
+      for (int m = 0; m < cnt[q]; ++m) {
+        const unsigned long long x = cq[m];     // broadcast read
+        ra += x < ca;
+        rb += x < cb;
+      }
+      if (ja < cnt[q] && ra < nsample) sq[ra] = (uint32_t)ca;
+      if (jb < cnt[q] && rb < nsample) sq[rb] = (uint32_t)cb;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < QB; ++q) Llo[q] = (ok[q] && lane < nsample) ? sel[q * 32 + lane] : 0xffffffffu;
+  __syncwarp();
+}
+
+constexpr int kKnnQB = 4;    // queries per warp pass
+
 __global__ void __launch_bounds__(kKnnThreads)
 knn_group_kernel(const float *__restrict__ pts, int N, int C,
                  const float *__restrict__ queries, int Q, int Cq, int nsample,
@@ -225,7 +307,8 @@ knn_group_kernel(const float *__restrict__ pts, int N, int C,
                  float *__restrict__ neighbors) {
   extern __shared__ float4 s_pt[];  // [N] (x, y, z, |p|^2)
   __shared__ float s_out[kKnnThreads / 32][32 * 3];
-  __shared__ unsigned long long s_cand[kKnnThreads / 32][kKnnCap];
+  __shared__ uint32_t s_sel[kKnnThreads / 32][kKnnQB * 32];
+  __shared__ unsigned long long s_cand[kKnnThreads / 32][kKnnQB * kKnnCap];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -240,40 +323,56 @@ knn_group_kernel(const float *__restrict__ pts, int N, int C,
   const int q_begin = blockIdx.y * q_per_cta;
   const int q_end = min(Q, q_begin + q_per_cta);
 
-  for (int q = q_begin + warp; q < q_end; q += kKnnThreads / 32) {
-    const float *c = queries + ((size_t)b * Q + q) * Cq;
-    const float cx = c[0], cy = c[1], cz = c[2];
-    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));  // utils.py:139
-    uint32_t Llo;   // lane l: index of the l-th nearest point by (distance, index)
-    if (N < 64 || !knn_select_twopass(s_pt, N, nsample, cx, cy, cz, c2, lane, s_cand[warp],
-                                      reinterpret_cast<uint32_t *>(s_out[warp]), Llo))
-      Llo = knn_select_stream(s_pt, N, nsample, cx, cy, cz, c2, lane);
-
-    const size_t row = (size_t)b * Q + q;
-    if (knn_idx && lane < nsample) knn_idx[row * nsample + lane] = (int64_t)Llo;
-    if (neighbors) {
-      if (C == 3) {
-        if (lane < nsample) {
-          const float4 P = s_pt[Llo];
-          const bool sub = lane < 3;  // utils.py:36 slices the SLOT axis: only slots 0,1,2 are centred
-          s_out[warp][lane * 3 + 0] = sub ? __fsub_rn(P.x, cx) : P.x;
-          s_out[warp][lane * 3 + 1] = sub ? __fsub_rn(P.y, cy) : P.y;
-          s_out[warp][lane * 3 + 2] = sub ? __fsub_rn(P.z, cz) : P.z;
-        }
-        __syncwarp();
-        float *o = neighbors + row * nsample * 3;
-        for (int t = lane; t < nsample * 3; t += 32) o[t] = s_out[warp][t];  // coalesced
-        __syncwarp();
-      } else {
-        float *o = neighbors + row * nsample * C;
-        for (int t0 = 0; t0 < nsample * C; t0 += 32) {
-          const int t = t0 + lane;
-          const int s = min(t / C, nsample - 1), ch = t % C;
-          const uint32_t j = __shfl_sync(kFull, Llo, s);
-          if (t < nsample * C) {
-            float v = p[(size_t)j * C + ch];
-            if (s < 3) v = __fsub_rn(v, c[ch]);
-            o[t] = v;
+  for (int q0 = q_begin + warp * kKnnQB; q0 < q_end; q0 += (kKnnThreads / 32) * kKnnQB) {
+    float cx[kKnnQB], cy[kKnnQB], cz[kKnnQB], c2[kKnnQB];
+#pragma unroll
+    for (int j = 0; j < kKnnQB; ++j) {
+      const int q = min(q0 + j, q_end - 1);      // a ragged tail repeats the last query (its outputs are skipped)
+      const float *c = queries + ((size_t)b * Q + q) * Cq;
+      cx[j] = c[0]; cy[j] = c[1]; cz[j] = c[2];
+      c2[j] = __fadd_rn(__fadd_rn(__fmul_rn(cx[j], cx[j]), __fmul_rn(cy[j], cy[j])), __fmul_rn(cz[j], cz[j]));  // utils.py:139
+    }
+    uint32_t Lq[kKnnQB];   // lane l: index of the l-th nearest point by (distance, index), per query
+    bool ok[kKnnQB];
+    if (N >= 64) {
+      knn_select_twopass_multi<kKnnQB>(s_pt, N, nsample, cx, cy, cz, c2, lane, s_cand[warp], s_sel[warp], Lq, ok);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kKnnQB; ++j) ok[j] = false;
+    }
+#pragma unroll
+    for (int j = 0; j < kKnnQB; ++j) {
+      const int q = q0 + j;
+      if (q >= q_end) continue;                  // warp-uniform
+      uint32_t Llo = Lq[j];
+      if (!ok[j]) Llo = knn_select_stream(s_pt, N, nsample, cx[j], cy[j], cz[j], c2[j], lane);   // heavy ties / tiny clouds
+      const size_t row = (size_t)b * Q + q;
+      if (knn_idx && lane < nsample) knn_idx[row * nsample + lane] = (int64_t)Llo;
+      if (neighbors) {
+        if (C == 3) {
+          if (lane < nsample) {
+            const float4 P = s_pt[Llo];
+            const bool sub = lane < 3;  // utils.py:36 slices the SLOT axis: only slots 0,1,2 are centred
+            s_out[warp][lane * 3 + 0] = sub ? __fsub_rn(P.x, cx[j]) : P.x;
+            s_out[warp][lane * 3 + 1] = sub ? __fsub_rn(P.y, cy[j]) : P.y;
+            s_out[warp][lane * 3 + 2] = sub ? __fsub_rn(P.z, cz[j]) : P.z;
+          }
+          __syncwarp();
+          float *o = neighbors + row * nsample * 3;
+          for (int t = lane; t < nsample * 3; t += 32) o[t] = s_out[warp][t];  // coalesced
+          __syncwarp();
+        } else {
+          const float *c = queries + row * Cq;
+          float *o = neighbors + row * nsample * C;
+          for (int t0 = 0; t0 < nsample * C; t0 += 32) {
+            const int t = t0 + lane;
+            const int s2 = min(t / C, nsample - 1), ch = t % C;
+            const uint32_t jj = __shfl_sync(kFull, Llo, s2);
+            if (t < nsample * C) {
+              float v = p[(size_t)jj * C + ch];
+              if (s2 < 3) v = __fsub_rn(v, c[ch]);
+              o[t] = v;
+            }
           }
         }
       }
@@ -332,10 +431,10 @@ static int launch_knn(const float *pts, int B, int N, int C, const float *querie
                       int nsample, int64_t *knn_idx, float *neighbors, cudaStream_t st) {
   if (B == 0 || Q == 0) return VPF_OK;
   const size_t smem = (size_t)N * sizeof(float4);
-  if (smem + 12 * 1024 > 48 * 1024)   // the kernel also holds ~11 KB of static shared memory (candidates, gather staging)
+  if (smem + 40 * 1024 > 48 * 1024)   // the kernel also holds ~37 KB of static shared memory (candidates, selections, gather staging)
     VPF_CUDA_TRY(cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // enough CTAs for >= 2 waves on small batches; a split re-stages the cloud (cheap)
-  const int warps = kKnnThreads / 32;
+  const int warps = (kKnnThreads / 32) * kKnnQB;     // queries one CTA handles per pass over the cloud
   int splits = ceil_div(2 * num_sms() * 4, B);
   splits = max(1, min(splits, ceil_div(Q, warps)));
   const int per = ceil_div(ceil_div(Q, splits), warps) * warps;
