@@ -428,11 +428,25 @@ def gemm_roofline(eng, load, pk, pk_kind, args):
         if d.get("pairs") == eng.b and d.get("config") == args.config:
             traffic = d["gemm"]["bytes_per_launch"]
             traffic_src = f"profiles/r02_step_dram.json (ncu, git {d.get('git', '?')}, {d['gemm']['launches']} launches)"
-    roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA)", "bound": "tensor", "achieved": ach, "peak": peak,
-            "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+    # which roof binds?  arithmetic intensity of the step's GEMMs against the machine's ridge point
+    hbm_peak = pk["hbm_gbs"]
+    ai, ridge = fl / ab, peak * 1e12 / (hbm_peak * 1e9)
+    ach_gbs = ab / t / 1e9
+    frac_tensor, frac_hbm = ach / peak, ach_gbs / hbm_peak
+    if ai < ridge:
+        bound, achieved, pk_val, unit, frac = "hbm", ach_gbs, hbm_peak, "GB/s", frac_hbm
+    else:
+        bound, achieved, pk_val, unit, frac = "tensor", ach, peak, "TFLOP/s", frac_tensor
+    roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA)", "bound": bound, "achieved": achieved, "peak": pk_val,
+            "unit": unit, "frac": frac,
+            "bound_rule": f"arithmetic intensity {ai:.0f} FLOP/B {'<' if ai < ridge else '>='} ridge {ridge:.0f} FLOP/B "
+                          "(sustained bf16 peak / measured copy bandwidth)",
+            "frac_tensor": frac_tensor, "achieved_tflops": ach, "peak_tflops": peak,
+            "frac_hbm": frac_hbm, "achieved_gbs": ach_gbs, "peak_gbs": hbm_peak,
+            "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
             "traffic_source": traffic_src, "algorithmic_bytes": ab / max(1, len(rec)),
             "algorithmic_bytes_unit": "bytes/launch (operands + result once; residual read)",
-            "peak_kind": pk_kind + " sustained (kernel timed inside a long step)",
+            "peak_kind": pk_kind + " (sustained bf16 matmul; copy bandwidth) -- kernel timed inside a long step",
             "launches_per_step": len(rec), "avg_launch_us": 1e6 * t / max(1, len(rec)), "gemm_ms_per_step": 1e3 * t,
             "gemm_flops_per_step": fl}
     return roof, launches
