@@ -122,6 +122,20 @@ __device__ __forceinline__ void mma_kmajor_kmajor(uint32_t tmem_d, uint32_t a_s,
 // bf16), and only then is that row of O rescaled in TMEM (tcgen05.ld -> multiply -> tcgen05.st) -- after the first key
 // block of a 2048-point cross-attention this almost never happens.  Softmax arithmetic per logit: max, fma, ex2, add,
 // 3 for the dropout bit, half a pack; the 1 / (1 - p) of dropout is folded into the final normalisation.
+#ifdef VPF_ATTN_TIMING
+// experiment-only build (VPF_NVCC_EXTRA=-DVPF_ATTN_TIMING): globaltimer stamps of CTA 0 (softmax warp 2 lane 0: slots 0..5
+// per block, MMA warp lane 0: slots 6..7), first 32 blocks
+__device__ unsigned long long g_attn_stamp[32][8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_STAMP(cond, n, slot) do { if ((cond) && (n) < 32) g_attn_stamp[n][slot] = gtime(); } while (0)
+#else
+#define ATT_STAMP(cond, n, slot) do { } while (0)
+#endif
+
 constexpr int kFwdThreads = 320;
 constexpr int kFOffQ = 0, kFOffKV = kTile, kFOffP = kFOffKV + 4 * kTile, kFOffX = kFOffP + 2 * kTile, kFOffBar = kFOffX + 512;
 constexpr int kFwdSmem = kFOffBar + 96;
@@ -139,6 +153,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 
 // rare path of the lazy running max: multiply this thread's 32 O columns (one TMEM lane) by corr.  Not inlined, so its
 // 32 registers do not add to the pressure of the softmax loop.
@@ -223,6 +245,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::mbar_wait(&kv_full[st], (n >> 1) & 1);
       ptx::mbar_wait(s_empty, (n & 1) ^ 1);
       ptx::tc_fence_after();
+      ATT_STAMP(blockIdx.x == 0 && lane == 0, n, 6);
       if (ptx::elect_one()) {
         mma_kmajor_kmajor(tmem_base, sQ, sKV + st * 2 * kTile, 4, ptx::umma_idesc_bf16(128, kv16, 0, 0), false);
         ptx::umma_commit(s_full);
@@ -238,6 +261,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::mbar_wait(p_full, n & 1);
       if (t == 0) ptx::mbar_wait(o_empty, (j & 1) ^ 1);      // the previous item's O has been read out of TMEM
       ptx::tc_fence_after();
+      ATT_STAMP(blockIdx.x == 0 && lane == 0, n, 7);
       if (ptx::elect_one()) {
         const uint32_t sV = sKV + st * 2 * kTile + kTile;
 #pragma unroll
@@ -263,6 +287,40 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t kq4 = (uint32_t)((Lk + 3) >> 2);
     const uint32_t prow = sP + hf * kTile;
     const uint32_t kthr = 0x7f7f7f7fu + dc.thr * 0x01010101u;
+    // The end of an item (wait for its last P.V, read O out of TMEM, normalise, store) is DEFERRED into the first block of
+    // the next item, behind that block's logit load / maximum exchange: the tensor-core latency of the last P.V and the
+    // skew between the eight softmax warps are hidden there instead of idling this CTA.  The two threads of a row
+    // exchange their partial row sums through two spare TMEM columns (192 + half), ordered by the p_full -> pv_full chain.
+    struct { bool on; int n, b, h, bh, qrow; float m, l; } pend = {false, 0, 0, 0, 0, 0, 0.f, 0.f};
+    auto epilogue = [&]() {
+      ptx::mbar_wait(pv_full, pend.n & 1);
+      ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, pend.n, 4);
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(t_row + 128 + hf * 32, o);
+      const float l_other = __uint_as_float(tmem_ld1(t_row + 192 + (hf ^ 1)));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_empty);
+      if (pend.qrow < Lq) {
+        const float tot = pend.l + l_other;
+        const float inv = dc.scale / tot;
+        bf16 *op = O + ((size_t)pend.b * Lq + pend.qrow) * ldo + pend.h * HD + hf * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          v.y = pack2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          v.z = pack2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          v.w = pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4 *>(op + 8 * c) = v;
+        }
+        if (hf == 0) LSE[(size_t)pend.bh * Lq + pend.qrow] = pend.m + log2f(tot);
+      }
+      ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, pend.n, 5);
+      pend.on = false;
+    };
     int n = 0, j = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
       const int bh = it / nqb, qb = it - bh * nqb, b = bh / H, h = bh - b * H;
@@ -273,8 +331,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int t = 0; t < nkb; ++t, ++n) {
         const int kvalid = min(128, Lk - t * 128);
         const int j0 = hf * 64;                         // this thread's key offset inside the block
+        ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, n, 0);
         ptx::mbar_wait(s_full, n & 1);
         ptx::tc_fence_after();
+        ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, n, 1);
         if (!active) {
           // no valid query row in this warp (tail query block): keep the pipeline protocol, skip the arithmetic; the
           // P rows stay whatever they were -- row m of P only reaches row m of O, which is never stored
@@ -282,7 +342,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) { ptx::mbar_arrive(s_empty); }
-          if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+          if (pend.on) epilogue();
+          else if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+          ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(p_full);
           continue;
@@ -316,6 +378,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         xm[hf * 128 + row] = __float2bfloat16(mx == -INFINITY ? -1e30f : bound);
         named_bar(1 + quad, 64);
         const float m_blk = fmaxf(__bfloat162float(xm[row]), __bfloat162float(xm[128 + row]));
+        ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, n, 2);
         bool need = t == 0 ? false : (m_blk > m + kLazy);
         if (t == 0) m = m_blk;
         if (__any_sync(0xffffffffu, need)) {
@@ -328,8 +391,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           l *= corr;
           m = m_new;
         }
-        // probabilities -> dropout -> bf16 P tile (written once the previous P.V has finished reading the tile)
-        if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+        // the previous item leaves TMEM here (its last P.V has had the whole load / exchange phase to finish); otherwise
+        // just make sure the previous P.V of this item has finished reading the P tile
+        if (pend.on) epilogue();
+        else if (n > 0) ptx::mbar_wait(pv_full, (n - 1) & 1);
+        // probabilities -> dropout -> bf16 P tile
         float lsum = 0.f;
         const float negm = -m;
         const uint32_t g4 = (uint32_t)((t * 128 + j0) >> 2);
@@ -363,43 +429,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) ptx::mbar_arrive(s_empty);
         if (kvalid == 128) half(sx, 1, false); else half(sx, 1, true);
         l += lsum;
+        if (t == nkb - 1) {      // this half's row sum for the other half's thread (read after this item's last pv_full)
+          tmem_st1(t_row + 192 + hf, __float_as_uint(l));
+          tmem_st_wait();
+        }
         ptx::tc_fence_before();
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_full);
+        ATT_STAMP(blockIdx.x == 0 && warp == 2 && lane == 0, n, 3);
       }
-      // ---- end of the item: read O, normalise, store
-      ptx::mbar_wait(pv_full, (n - 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t o[32];
-      ptx::tmem_ld_32x32(t_row + 128 + hf * 32, o);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(o_empty);
-      // row sum: the two threads of a row exchange their halves through 4 bytes of the row's own (now idle) P segment
-      float *xl = reinterpret_cast<float *>(smem + kFOffP + row * 128);
-      if (hf == 1) *xl = l;
-      named_bar(1 + quad, 64);
-      float tot = 0.f;
-      if (hf == 0) { tot = l + *xl; *xl = tot; }
-      named_bar(1 + quad, 64);
-      if (hf == 1) tot = *xl;
-      if (qrow < Lq) {
-        const float inv = dc.scale / tot;
-        bf16 *op = O + ((size_t)b * Lq + qrow) * ldo + h * HD + hf * 32;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 v;
-          v.x = pack2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-          v.y = pack2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-          v.z = pack2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-          v.w = pack2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-          *reinterpret_cast<uint4 *>(op + 8 * c) = v;
-        }
-        if (hf == 0) LSE[(size_t)bh * Lq + qrow] = m + log2f(tot);
-      }
+      pend.on = true; pend.n = n - 1; pend.b = b; pend.h = h; pend.bh = bh; pend.qrow = qrow; pend.m = m; pend.l = l;
     }
+    if (pend.on) epilogue();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -780,3 +822,11 @@ int attention_tc_bwd(const void *Q, int ldq, const void *K, const void *V, int l
 
 }  // namespace atc
 }  // namespace vpf
+
+#ifdef VPF_ATTN_TIMING
+extern "C" int vpf_debug_attn_stamps(unsigned long long *out256) {
+  VPF_CUDA_TRY(cudaDeviceSynchronize());
+  VPF_CUDA_TRY(cudaMemcpyFromSymbol(out256, vpf::atc::g_attn_stamp, sizeof(unsigned long long) * 256));
+  return VPF_OK;
+}
+#endif
