@@ -242,6 +242,28 @@ int vpf_scale_by(const float *x, const float *s, float *out, long long n, void *
 /* dst[r, c] = alpha * src[r, c] over a [rows, cols] window of two row-strided fp32 arrays (padded head buffers). */
 int vpf_copy2d(const float *src, int lds, float *dst, int ldd, long long rows, int cols, float alpha, void *stream);
 
+/* ------------------------------------------------------------------ part segmentation
+ * PointNetFeaturePropagation, utils.py:192-242: three nearest of the S centres for every point, ordered by (distance
+ * ascending, index ascending), inverse-distance weights w = (1 / (d + 1e-8)) / sum. */
+int vpf_three_nn(const float *pts, const float *centers, int B, int N, int S, int *idx, float *w, void *stream);
+/* interpolated[b*N + n, :C] = sum_j w_j * feats[b*S + idx_j, :C] (utils.py:230), bf16, into a GEMM operand of row stride
+ * ldo >= C + 8 whose columns C..C+2 receive the point coordinates (the cat of utils.py:233-234) and the rest zeros. */
+int vpf_interp3_fwd(const void *feats_bf16, int ldf, const int *idx, const float *w, const float *pts, void *out_bf16,
+                    int ldo, int B, int N, int S, int C, void *stream);
+int vpf_interp3_bwd(const void *dout_bf16, int ldo, const int *idx, const float *w, float *dfeats, int ldd, int B, int N,
+                    int S, int C, void *stream);
+/* x.max(2), x.mean(2) over the groups (partseg.py:432-434) on a bf16 [B, L, ld] tensor; the backward ACCUMULATES. */
+int vpf_token_pool_bf16_fwd(const void *x_bf16, int ld, float *out, int *argmax, int B, int L, int C, void *stream);
+int vpf_token_pool_accum_bwd(const float *dout, const int *argmax, float *dx, int ld, int B, int L, int C, void *stream);
+/* nn.LeakyReLU(slope), partseg.py:393. */
+int vpf_leaky_relu_fwd(const float *x, float *y, float slope, long long n, void *stream);
+int vpf_leaky_relu_bwd(const float *dy, const float *x, float *dx, float slope, long long n, void *stream);
+/* first propagation Conv1d weight [Co, 3 + C] (xyz first) -> bf16 operand [Co, ldo] with the xyz columns moved behind the C
+ * feature columns, and the inverse (+=) for its gradient. */
+int vpf_permute_w(const float *W, void *Wout_bf16, int Co, int C, int ldo, void *stream);
+int vpf_unpermute_dw(const float *dWp, float *dW, int Co, int C, int ldo, void *stream);
+int vpf_copy2d_bf16(const void *src, int lds, void *dst, int ldd, long long rows, int cols, void *stream);
+
 /* ------------------------------------------------------------------ loss + optimiser
  * NT-Xent (lightly 1.1.21 NTXentLoss; call sites pretrain.py:155,196,202). */
 int vpf_l2norm_rows(const float *x, float *z, float *norm, int n, int D, void *stream);

@@ -67,6 +67,17 @@ def _max1(x, name):
     return val
 
 
+def _leaky(x, slope, name):
+    if _CH is None:
+        return F.leaky_relu(x, slope)
+    name = _CH.prefix + name
+    _CH.rec[name] = (x > 0).detach()
+    if name in _CH.pins:
+        m = _CH.pins[name].reshape(x.shape).to(x.dtype)
+        return x * (m + slope * (1 - m))
+    return F.leaky_relu(x, slope)
+
+
 _PREFIX = [""]
 
 
@@ -269,6 +280,85 @@ def pc_ft_forward(sd, pts, start_idx, G, S, H, n_sa, training=True, running_out=
         x = encoder(sd, "encoder", group_embs, pos_embs, pts_embs, H, n_sa)
         backbone = torch.cat([_max1(x, "pool.max"), x.mean(1)], 1)
         return finetune_head(sd, "finetune_head", backbone, training, running_out)
+
+
+def encoder_taps(sd, k, group_embs, pos_embs, pts_embs, H, n_sa, layer_idx):
+    """Encoder.forward with modal_prior=False, partseg.py:314-341: the outputs of self-attention layers i+1 in layer_idx."""
+    x = ca_layer(sd, k + ".cross_attn_1", group_embs + pos_embs, pts_embs, H)
+    feats = []
+    for i in range(n_sa):
+        x = sa_layer(sd, f"{k}.sa_layers.{i}", x + pos_embs, H)
+        if i + 1 in layer_idx:
+            feats.append(x)
+    return feats
+
+
+def three_nn(xyz1, xyz2):
+    """PointNetFeaturePropagation's neighbour search, utils.py:223-229 with square_distance (utils.py:138-140) written out:
+    xyz1 [B,N,3], xyz2 [B,S,3] -> (idx [B,N,3] int64, weight [B,N,3]).  Pin name "nn3" replaces idx (weights follow it)."""
+    B, N, _ = xyz1.shape
+    dist = -2 * torch.matmul(xyz1, xyz2.permute(0, 2, 1))
+    dist = dist + torch.sum(xyz1 ** 2, -1).view(B, N, 1)
+    dist = dist + torch.sum(xyz2 ** 2, -1).view(B, 1, -1)
+    d, idx = dist.sort(dim=-1)
+    d, idx = d[:, :, :3], idx[:, :, :3]
+    if _CH is not None:
+        name = _CH.prefix + "nn3"
+        _CH.rec[name] = idx.detach()
+        if name in _CH.pins:
+            idx = _CH.pins[name].reshape(idx.shape).long()
+            d = dist.gather(2, idx)
+    r = 1.0 / (d + 1e-8)
+    return idx, r / r.sum(2, keepdim=True)
+
+
+def feature_propagation(sd, k, pts, center, x, training, running_out=None):
+    """PointNetFeaturePropagation.forward, utils.py:205-242, rows x channels: pts [B,N,3], center [B,S,3], x [B,S,C]
+    (points1 = the xyz of every point, partseg.py:450) -> [B*N, 1024]."""
+    B, N, _ = pts.shape
+    idx, w = three_nn(pts, center)
+    gathered = torch.stack([x[b][idx[b]] for b in range(B)])                  # index_points: [B, N, 3, C]
+    interp = (gathered * w.view(B, N, 3, 1)).sum(2)
+    f = torch.cat([pts, interp], -1).reshape(B * N, -1)                       # cat([points1, interpolated]), utils.py:234
+    for i in range(2):
+        f = F.linear(f, sd[f"{k}.mlp_convs.{i}.weight"][:, :, 0], sd[f"{k}.mlp_convs.{i}.bias"])
+        f = _relu(_bn(sd, f"{k}.mlp_bns.{i}", f, training, running_out), f"seg.relu_p{i + 1}")
+    return f
+
+
+def partseg_forward(sd, pts, cls_onehot, start_idx, G, S, H, n_sa, layer_idx, training=True, running_out=None,
+                    tokenizer=None):
+    """CrossFormer_partseg.forward, partseg.py:407-470 (max_dpr = 0: DropPath is the identity) -> [B, N, num_part_classes].
+    Conv1d(kernel 1) layers are written as linear maps over rows = points; dp1's mask comes from `with dropout(...)` under the
+    key "seg.dp1" (rows x 512 channels, element index row * 512 + channel), else it is the identity."""
+    with _prefix("seg."):
+        B, N, _ = pts.shape
+        pts_embs = input_adapter(sd, "input_adapter", pts)
+        if tokenizer is not None:
+            nb, ce = tokenizer(pts.detach(), G, S, start_idx)
+        else:
+            nb, ce = T.divide_patches(pts.detach().numpy(), G, S, np.asarray(start_idx))
+            nb, ce = torch.from_numpy(nb).to(pts.dtype), torch.from_numpy(ce).to(pts.dtype)
+        group_embs = group2emb(sd, "group2emb", nb, training, running_out)
+        pos_embs = position_emb(sd, "position_emb", ce)
+        feats = encoder_taps(sd, "encoder", group_embs, pos_embs, pts_embs, H, n_sa, layer_idx)
+        x = torch.cat([_ln(sd, "norm", f) for f in feats], -1)                # [B, G, k*D]  (:422-428)
+        x_max, x_avg = _max1(x, "seg.max"), x.mean(1)                         # :430-434
+        lab = F.linear(cls_onehot.view(B, 16).to(pts.dtype), sd["label_conv.0.weight"][:, :, 0])
+        lab = _leaky(_bn(sd, "label_conv.1", lab, training, running_out), 0.2, "seg.leaky")      # :391-393, :441-443
+        glob = torch.cat([x_max, x_avg, lab], 1)                              # [B, 2kD + 64], repeated over the points
+        f0 = feature_propagation(sd, "propagation", pts, ce, x, training, running_out)           # [B*N, 1024]
+        h = torch.cat([f0, glob.unsqueeze(1).expand(-1, N, -1).reshape(B * N, -1)], 1)           # :452
+        h = F.linear(h, sd["conv1.weight"][:, :, 0], sd["conv1.bias"])
+        h = _relu(_bn(sd, "bn1", h, training, running_out), "seg.relu1")
+        if _DROP is not None and training:
+            from . import rng as R
+            m = R.residual_keep(_DROP["seed"], _DROP["op_bases"]["seg.dp1"], 0.5, B * N, 512)
+            h = h * torch.from_numpy(m).to(h.dtype)
+        h = F.linear(h, sd["conv2.weight"][:, :, 0], sd["conv2.bias"])
+        h = _relu(_bn(sd, "bn2", h, training, running_out), "seg.relu2")
+        h = F.linear(h, sd["conv3.weight"][:, :, 0], sd["conv3.bias"])
+        return h.view(B, N, -1)
 
 
 def cross_entropy_ls(logits, labels, eps=0.2):

@@ -118,6 +118,43 @@ def ft_inputs(cfg):
     return torch.from_numpy(pts), start, labels
 
 
+SEG_CASES = {
+    # part-segmentation fixtures (ft_partseg.py: 16 object classes, 50 part classes)
+    "seg_small": dict(D=128, H=2, n_sa=4, G=32, S=8, N=128, MR=2, b=4, layer_idx=[1, 2, 4], parts=50, seed=71),
+    "seg_cfgA": dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, b=4, layer_idx=[2, 5, 8], parts=50, seed=72),
+}
+
+
+def build_seg_model(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
+    """CrossFormer_partseg with the kwargs of the reference's utils.build_ft_partseg (utils.py:277-298); max_dpr = 0."""
+    import importlib
+
+    import torch
+
+    pcmod = importlib.import_module(pkg + ".model.pointcloud")
+    part = importlib.import_module(pkg + ".model.pointcloud.partseg")
+    torch.manual_seed(cfg["seed"])
+    ad = pcmod.PointCloudInputAdapter(pointcloud_shape=(cfg["N"], 3), num_input_channels=cfg["D"])
+    return part.CrossFormer_partseg(input_adapter=ad, num_latents=cfg["G"], num_latent_channels=cfg["D"], group_size=cfg["S"],
+                                    num_cross_attention_layers=1, num_cross_attention_heads=cfg["H"],
+                                    num_self_attention_layers=cfg["n_sa"], num_self_attention_heads=cfg["H"],
+                                    mlp_widen_factor=cfg["MR"], max_dpr=0.0, atten_drop=atten_drop, mlp_drop=mlp_drop,
+                                    layer_idx=list(cfg["layer_idx"]), num_part_classes=cfg["parts"])
+
+
+def seg_inputs(cfg):
+    """-> (pts [b,N,3], FPS start [b], one-hot object class [b,16], part labels [b,N])  (ft_partseg.py:146-160)."""
+    import torch
+
+    pts = make_clouds("randn", cfg["b"], cfg["N"], cfg["seed"] + 1)
+    start = make_start(cfg["b"], cfg["N"], cfg["seed"])
+    g = torch.Generator().manual_seed(cfg["seed"] + 3)
+    obj = torch.randint(0, 16, (cfg["b"],), generator=g)
+    onehot = torch.nn.functional.one_hot(obj, 16).float()
+    labels = torch.randint(0, cfg["parts"], (cfg["b"], cfg["N"]), generator=g)
+    return torch.from_numpy(pts), start, onehot, labels
+
+
 def perturb_state_dict(sd, seed):
     """Deterministic perturbation so LayerNorm/BatchNorm affine terms and biases are not at their trivial init."""
     import torch

@@ -137,6 +137,62 @@ def run_ft_case(name, cfg):
     print("ft model", name, "loss", out["loss"], "logits", out["logits"].shape, "params with grad", len(names))
 
 
+def run_seg_case(name, cfg):
+    """CrossFormer_partseg + CrossEntropyLoss(label_smoothing=0.2) over every point (partseg.py:345-470, ft_partseg.py:128,
+    158-160) from the REAL reference (max_dpr = 0, pinned FPS start, sorted kNN): logits, loss, gradient norms, a few full
+    gradients, updated running statistics."""
+    _refshim.load()
+    import vipformer.model.pointcloud.utils as U
+
+    ref = _synth.build_seg_model(cfg, pkg="vipformer")
+    mine = _synth.build_seg_model(cfg, pkg="vipformer_b200")
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys()), "part-segmentation state_dict keys differ from the reference"
+    for k in rs:
+        assert rs[k].shape == ms[k].shape and torch.equal(rs[k], ms[k]), f"state_dict value differs at {k}"
+    ref.load_state_dict(_synth.perturb_state_dict(ref.state_dict(), cfg["seed"] + 10))
+    ref.train()
+    ref.dp1.p = 0.0          # nn.Dropout(0.5) draws from torch's RNG: off for the fixture (masks are tested on the GPU side)
+    pts, start, onehot, labels = _synth.seg_inputs(cfg)
+
+    class _T:
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+    proxy = _T()
+    proxy.randint = _PinnedRandint(start)
+    orig_torch, orig_knn = U.torch, U.knn_point
+
+    def knn_sorted(nsample, xyz, new_xyz):
+        d = U.square_distance(new_xyz, xyz)
+        return torch.topk(d, nsample, dim=-1, largest=False, sorted=True)[1]
+
+    try:
+        U.torch, U.knn_point = proxy, knn_sorted
+        logits = ref(pts, onehot)
+    finally:
+        U.torch, U.knn_point = orig_torch, orig_knn
+    loss = torch.nn.CrossEntropyLoss(label_smoothing=0.2)(logits.reshape(-1, cfg["parts"]), labels.reshape(-1))
+    loss.backward()
+    out = dict(logits=logits.detach().numpy().astype(np.float16) if cfg["N"] > 512 else logits.detach().numpy(),
+               loss=np.array([loss.item()]))
+    names, norms = [], []
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(p.grad.double().norm().item())
+        if k in FULL_GRADS or k in ("conv3.weight", "conv3.bias", "norm.weight", "label_conv.0.weight",
+                                    "propagation.mlp_convs.0.bias", "bn1.weight"):
+            out[f"grad::{k}"] = p.grad.numpy()
+    out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms)
+    for k, v in ref.state_dict().items():
+        if "running_" in k:
+            out[f"buf::{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, f"model_{name}.npz"), **out)
+    print("seg model", name, "loss", out["loss"], "logits", out["logits"].shape, "params with grad", len(names))
+
+
 def main(what):
     torch.set_num_threads(8)
     if "model" in what:
@@ -145,7 +201,10 @@ def main(what):
     if "ft" in what:
         for name, cfg in _synth.FT_CASES.items():
             run_ft_case(name, cfg)
+    if "seg" in what:
+        for name, cfg in _synth.SEG_CASES.items():
+            run_seg_case(name, cfg)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["model", "ft"])
+    main(sys.argv[1:] or ["model", "ft", "seg"])

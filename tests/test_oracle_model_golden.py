@@ -147,3 +147,54 @@ def test_finetune_oracle_matches_reference(name, golden_dir):
                 assert np.array_equal(g[key], o["sd"][k].numpy()), k
             else:
                 assert _rel(o["run"][k], g[key]) < 1e-4, k
+
+
+def oracle_seg_run(cfg, pins=None, drop=None, dtype=torch.float32):
+    """Part-segmentation oracle run shared with the GPU tests: mirror init -> perturbed state_dict -> oracle forward,
+    label-smoothed CE over all points (eps 0.2, ft_partseg.py:128,160), backward."""
+    import contextlib
+
+    model = _synth.build_seg_model(cfg)
+    sd = {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in _synth.perturb_state_dict(model.state_dict(), cfg["seed"] + 10).items()}
+    names = [k for k, _ in model.named_parameters()]
+    for k in names:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    for k in list(sd.keys()):
+        if ".cross_attn_n." in k:
+            sd[k.replace(".cross_attn_n.", ".cross_attn_1.")] = sd[k]
+    pts, start, onehot, labels = _synth.seg_inputs(cfg)
+    run = {}
+    with M.choices(pins) as ch, (M.dropout(**drop) if drop else contextlib.nullcontext()):
+        logits = M.partseg_forward(sd, pts.to(dtype), onehot.to(dtype), start, cfg["G"], cfg["S"], cfg["H"], cfg["n_sa"],
+                                   cfg["layer_idx"], True, run)
+        loss = M.cross_entropy_ls(logits.reshape(-1, cfg["parts"]), labels.reshape(-1), 0.2)
+        loss.backward()
+    return dict(sd=sd, names=names, logits=logits.detach(), loss=loss.item(), run=run, rec=ch.rec,
+                inputs=(pts, start, onehot, labels))
+
+
+@pytest.mark.parametrize("name", ["seg_small", "seg_cfgA"])
+def test_partseg_oracle_matches_reference(name, golden_dir):
+    """CrossFormer_partseg + CrossEntropyLoss(label_smoothing=0.2): oracle restatement vs vectors from the REAL reference."""
+    cfg = _synth.SEG_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    torch.set_num_threads(8)
+    o = oracle_seg_run(cfg)
+    gl = torch.from_numpy(g["logits"].astype(np.float32))
+    assert _rel(o["logits"], gl) < (1e-3 if g["logits"].dtype == np.float16 else 1e-4)
+    assert abs(o["loss"] - float(g["loss"][0])) < 1e-4
+    gnames = list(g["grad_names"])
+    assert set(gnames) == {k for k in o["names"] if o["sd"][k].grad is not None}
+    norms = {k: o["sd"][k].grad.double().norm().item() for k in gnames}
+    ref = dict(zip(gnames, g["grad_norms"]))
+    mx = max(ref.values())
+    for k in gnames:
+        assert abs(norms[k] - ref[k]) <= 2e-3 * ref[k] + 1e-5 * mx, k
+    for key in g.files:
+        if key.startswith("grad::"):
+            k = key.split("::")[1]
+            # fp32 on both sides; the weights in front of the first train-mode BatchNorm see the most cancellation (2.1e-3)
+            assert _rel(o["sd"][k].grad, g[key]) < 4e-3 or np.abs(g[key]).max() < 1e-5 * mx, k
+        if key.startswith("buf::"):
+            k = key.split("::")[1]
+            assert _rel(o["run"][k], g[key]) < 1e-4, k

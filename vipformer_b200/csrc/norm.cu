@@ -845,7 +845,7 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
   else if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && y_bf16) bn_apply_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (bf16 *)y, relu, total, C);
   else if (!x_bf16 && !y_bf16) bn_apply_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, scale, shift, (float *)y, relu, total, C);
-  else return fail(VPF_EINVAL, "bn_apply: bf16 -> fp32 unsupported");
+  else bn_apply_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (float *)y, relu, total, C);
   return check_launch("bn_apply_kernel");
 }
 

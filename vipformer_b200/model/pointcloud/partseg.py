@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from ... import functional as Fn
+from ... import functional_seg as FnS
 from ... import _lib, ops, params
 from .classifier import InputAdapter, PointCloudInputAdapter  # noqa: F401
 from .utils import Group2Emb, PointNetFeaturePropagation, Sequential, divide_patches  # noqa: F401  (as the reference)
@@ -243,7 +244,9 @@ class _EncoderFn(torch.autograd.Function):
     (Encoder.forward, partseg.py:314-342).  One autograd node; explicit kernel-sequence backward."""
 
     @staticmethod
-    def forward(ctx, x_q, pos, kv, anchor, enc):
+    def forward(ctx, x_q, pos, kv, anchor, enc, taps=None):
+        """taps: None -> the last layer's output; a tuple of 1-based self-attention layer numbers -> the outputs of
+        exactly those layers (Encoder.forward with modal_prior=False, partseg.py:328-340), as a tuple."""
         _lib.require_cuda(x_q)
         root = getattr(enc, "root", enc)
         arena = _root_prepare(root, x_q.device)
@@ -267,28 +270,51 @@ class _EncoderFn(torch.autograd.Function):
             cfg = ca._cfg(B, L, Lk)
             x, c = Fn.ca_layer_fwd(x, pos2, kv2, ca._weights(), cfg, seed, ca._op_base + off, save)
             ctxs.append((ca, cfg, c, ca._op_base + off))
-        for layer in enc.sa_layers:
+        outs, tap_at = [], []
+        n_run = len(enc.sa_layers) if taps is None else (max(taps) if taps else 0)
+        for i, layer in enumerate(enc.sa_layers):
+            if i >= n_run:       # layers behind the last tap do not reach any output (the reference runs them for nothing)
+                break
             cfg = layer._cfg(B, L)
             x, c = Fn.sa_layer_fwd(x, pos2, layer._weights(), cfg, seed, layer._op_base + off, save)
             ctxs.append((layer, cfg, c, layer._op_base + off))
+            if taps is not None and (i + 1) in taps:
+                outs.append(x.view(B, L, D))
+                tap_at.append(len(ctxs) - 1)
+        ctx.tap_at = tap_at if taps is not None else None
         if save:
             ctx.ctxs, ctx.arena, ctx.has_pos = ctxs, arena, pos2 is not None
             ctx.pos_shape = None if pos is None else pos.shape
             ctx.kv_shape = None if kv is None else kv.shape
             ctx.kv_dtype = None if kv is None else kv.dtype
             ctx.seed, ctx.shape = seed, (B, L, D)
+        if taps is not None:
+            return tuple(outs)
         return x.view(B, L, D)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, *douts):
         B, L, D = ctx.shape
         ctx.arena.ensure_grads()
-        dx = _as_f32_2d(dout, D)
+        dev = next(d for d in douts if d is not None).device
+        tap_grads = {}
+        if ctx.tap_at is None:
+            dx = _as_f32_2d(douts[0], D)
+        else:        # gradient of tap j enters the chain behind the layer that produced it
+            dx = None
+            for pos_i, d in zip(ctx.tap_at, douts):
+                if d is not None:
+                    tap_grads[pos_i] = _as_f32_2d(d, D)
         dpos = None
         if ctx.has_pos:
-            dpos = ops.zeros_(torch.empty(ctx.pos_shape, dtype=F32, device=dout.device))
+            dpos = ops.zeros_(torch.empty(ctx.pos_shape, dtype=F32, device=dev))
         dkv = None
-        for layer, cfg, c, op_base in reversed(ctx.ctxs):
+        for li in range(len(ctx.ctxs) - 1, -1, -1):
+            layer, cfg, c, op_base = ctx.ctxs[li]
+            if li in tap_grads:
+                dx = tap_grads[li] if dx is None else ops.add_scale(dx, tap_grads[li], 1.0)
+            if dx is None:       # nothing flows into this layer (no tap at or behind it)
+                continue
             if isinstance(layer, CrossAttentionLayer):
                 dx, dkv = Fn.ca_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, op_base, dpos)
             else:
@@ -298,7 +324,7 @@ class _EncoderFn(torch.autograd.Function):
             dkv = dkv.view(ctx.kv_shape)
             if not ctx.needs_input_grad[2]:
                 dkv = None
-        return dx.view(B, L, D), dpos, dkv, None, None
+        return dx.view(B, L, D), dpos, dkv, None, None, None
 
 
 class Encoder(nn.Module):
@@ -340,8 +366,11 @@ class Encoder(nn.Module):
         """partseg.py:314-342.  group_embs [B,G,D], pos_embs [B,G,D] or [1,G,D], pts_embs [B,N,D] -> [B,G,D]."""
         if pad_mask is not None:
             raise NotImplementedError("pad_mask is always None on the ViPFormer path and is not implemented")
-        if not self.modal_prior:
-            raise NotImplementedError("modal_prior=False (per-layer feature taps, part segmentation) is a later scope row")
+        if not self.modal_prior:     # partseg.py:336-340: the outputs of the self-attention layers named in layer_idx
+            taps = tuple(int(i) for i in layer_idx)
+            if not taps or min(taps) < 1 or max(taps) > len(self.sa_layers) or list(taps) != sorted(set(taps)):
+                raise ValueError("layer_idx must be a strictly increasing list of self-attention layer numbers (1-based)")
+            return list(_EncoderFn.apply(group_embs, pos_embs, pts_embs, _anchor(self), self, taps))
         return _EncoderFn.apply(group_embs, pos_embs, pts_embs, _anchor(self), self)
 
 
@@ -565,6 +594,129 @@ class CrossFormer_pc_mp_ft(CrossFormer_pc_mp):
 
     def forward(self, pts):
         return self.finetune_head(self._tokens(pts))
+
+
+class _PartSegHeadFn(torch.autograd.Function):
+    """Everything of CrossFormer_partseg.forward behind the encoder taps (partseg.py:420-468) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, pts, center, cls_label, anchor, mod, *taps):
+        _lib.require_cuda(pts)
+        arena = _root_prepare(mod, pts.device)
+        B, N, _ = pts.shape
+        G, D = taps[0].shape[1], taps[0].shape[2]
+        cfg = NS(B=B, N=N, G=G, D=D, P=mod.conv3.out_channels, p_dp1=mod.dp1.p)
+        W, bn = mod._head_weights()
+        save = any(ctx.needs_input_grad)
+        seed = _StepState.seed_ptr(pts.device)
+        off = _rt.next_op_offset(arena.managed) if mod.training else 0
+        logits, c = FnS.partseg_head_fwd([_as_f32_2d(t, D) for t in taps], pts.float().contiguous(), center.float().contiguous(),
+                                         cls_label.reshape(B, -1), W, bn, cfg, mod.training, seed, mod._op_base + off, save)
+        _rt.tap("seg_head", c)
+        if mod.training:
+            for m in (mod.label_conv[1], mod.propagation.mlp_bns[0], mod.propagation.mlp_bns[1], mod.bn1, mod.bn2):
+                _bump(m)
+        if save:
+            ctx.c, ctx.mod, ctx.arena, ctx.W, ctx.cfg, ctx.seed, ctx.op = c, mod, arena, W, cfg, seed, mod._op_base + off
+        return logits.view(B, N, cfg.P)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.arena.ensure_grads()
+        cfg = ctx.cfg
+        d2 = dlogits.float().reshape(cfg.B * cfg.N, cfg.P)
+        if d2.stride(1) != 1:
+            d2 = d2.contiguous()
+        dtaps = FnS.partseg_head_bwd(d2, ctx.c, ctx.W, ctx.mod._head_grads(), cfg, ctx.seed, ctx.op)
+        ctx.c = None
+        return (None, None, None, None, None) + tuple(d.view(cfg.B, cfg.G, cfg.D) for d in dtaps)
+
+
+class CrossFormer_partseg(nn.Module):
+    """partseg.py:345-470.  forward(pts [B,N,3], cls_label [B,16]) -> part logits [B, N, num_part_classes].
+    DropPath is not built: construct with max_dpr = 0.0 (the reference's default 0.1 raises here)."""
+
+    def __init__(self, input_adapter=None, num_latents=128, num_latent_channels=384, group_size=32,
+                 num_cross_attention_layers=1, num_cross_attention_heads=6, num_self_attention_layers=12,
+                 num_self_attention_heads=6, mlp_widen_factor=4, max_dpr=0.1, atten_drop=.0, mlp_drop=.0, layer_idx=[],
+                 num_part_classes=50):
+        super().__init__()
+        D = num_latent_channels
+        self.num_groups = num_latents
+        self.group_size = group_size
+        self.group2emb = Group2Emb(D)
+        self.position_emb = _PositionEmb(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, D))
+        self.input_adapter = input_adapter
+        dpr_list = [x.item() for x in torch.linspace(0, max_dpr, num_self_attention_layers)]
+        self.encoder = Encoder(num_latent_channels=D, num_cross_attention_layers=num_cross_attention_layers,
+                               num_cross_attention_heads=num_cross_attention_heads,
+                               cross_attention_widening_factor=mlp_widen_factor,
+                               num_self_attention_layers=num_self_attention_layers,
+                               num_self_attention_heads=num_self_attention_heads,
+                               self_attention_widening_factor=mlp_widen_factor, dpr_list=dpr_list, atten_drop=atten_drop,
+                               mlp_drop=mlp_drop)
+        self.layer_idx = layer_idx
+        self.norm = nn.LayerNorm(D)
+        self.label_conv = nn.Sequential(nn.Conv1d(16, 64, kernel_size=1, bias=False), nn.BatchNorm1d(64), nn.LeakyReLU(0.2))
+        self.num_layer_idx = len(layer_idx)
+        self.propagation = PointNetFeaturePropagation(in_channel=self.num_layer_idx * D + 3, mlp=[mlp_widen_factor * D, 1024])
+        self.conv1 = nn.Conv1d(2 * self.num_layer_idx * D + 64 + 1024, 512, 1)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.dp1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(512, 256, 1)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.conv3 = nn.Conv1d(256, num_part_classes, 1)
+        self.relu = nn.ReLU()
+        self.fps_start_idx = None
+        self.fps_generator = None
+        _LayerBase._op_counter += 8
+        self._op_base = _LayerBase._op_counter       # dropout stream of dp1
+
+    def _head_weights(self):
+        wb, pr = params.wb, self.propagation
+        k, D = self.num_layer_idx, self.norm.normalized_shape[0]
+        W = NS(ln_w=self.norm.weight, ln_b=self.norm.bias, lc_w=wb(self.label_conv[0].weight).view(64, 16),
+               lc_bn_w=self.label_conv[1].weight, lc_bn_b=self.label_conv[1].bias,
+               p1_w_f32=pr.mlp_convs[0].weight.view(-1, k * D + 3), p1_b=pr.mlp_convs[0].bias,
+               p1_bn_w=pr.mlp_bns[0].weight, p1_bn_b=pr.mlp_bns[0].bias,
+               p2_w=wb(pr.mlp_convs[1].weight).view(1024, -1), p2_b=pr.mlp_convs[1].bias,
+               p2_bn_w=pr.mlp_bns[1].weight, p2_bn_b=pr.mlp_bns[1].bias,
+               c1_w=wb(self.conv1.weight).view(512, -1), c1_b=self.conv1.bias, bn1_w=self.bn1.weight, bn1_b=self.bn1.bias,
+               c2_w=wb(self.conv2.weight).view(256, 512), c2_b=self.conv2.bias, bn2_w=self.bn2.weight, bn2_b=self.bn2.bias,
+               c3_w=wb(self.conv3.weight).view(-1, 256), c3_b=self.conv3.bias)
+        bn = NS(lc_rm=self.label_conv[1].running_mean, lc_rv=self.label_conv[1].running_var,
+                p1_rm=pr.mlp_bns[0].running_mean, p1_rv=pr.mlp_bns[0].running_var, p2_rm=pr.mlp_bns[1].running_mean,
+                p2_rv=pr.mlp_bns[1].running_var, rm1=self.bn1.running_mean, rv1=self.bn1.running_var,
+                rm2=self.bn2.running_mean, rv2=self.bn2.running_var)
+        return W, bn
+
+    def _head_grads(self):
+        pr = self.propagation
+        k, D = self.num_layer_idx, self.norm.normalized_shape[0]
+        return NS(ln_w=self.norm.weight.grad, ln_b=self.norm.bias.grad, lc_w=self.label_conv[0].weight.grad.view(64, 16),
+                  lc_bn_w=self.label_conv[1].weight.grad, lc_bn_b=self.label_conv[1].bias.grad,
+                  p1_w=pr.mlp_convs[0].weight.grad.view(-1, k * D + 3), p1_b=pr.mlp_convs[0].bias.grad,
+                  p1_bn_w=pr.mlp_bns[0].weight.grad, p1_bn_b=pr.mlp_bns[0].bias.grad,
+                  p2_w=pr.mlp_convs[1].weight.grad.view(1024, -1), p2_b=pr.mlp_convs[1].bias.grad,
+                  p2_bn_w=pr.mlp_bns[1].weight.grad, p2_bn_b=pr.mlp_bns[1].bias.grad,
+                  c1_w=self.conv1.weight.grad.view(512, -1), c1_b=self.conv1.bias.grad, bn1_w=self.bn1.weight.grad,
+                  bn1_b=self.bn1.bias.grad, c2_w=self.conv2.weight.grad.view(256, 512), c2_b=self.conv2.bias.grad,
+                  bn2_w=self.bn2.weight.grad, bn2_b=self.bn2.bias.grad, c3_w=self.conv3.weight.grad.view(-1, 256),
+                  c3_b=self.conv3.bias.grad)
+
+    def forward(self, pts, cls_label):
+        if self.__dict__.get("_vpf_root") is None:
+            _set_root(self)
+        if self.num_layer_idx < 1:
+            raise ValueError("CrossFormer_partseg needs a non-empty layer_idx")
+        pts = pts.float().contiguous()
+        pts_embs = self.input_adapter(pts)
+        neighborhood, center = divide_patches(pts, self.num_groups, self.group_size, start_idx=self.fps_start_idx,
+                                              generator=self.fps_generator)
+        group_embs = self.group2emb(neighborhood)
+        pos_embs = self.position_emb(center)
+        feature_list = self.encoder(group_embs, pos_embs, pts_embs, self.layer_idx)
+        return _PartSegHeadFn.apply(pts, center, cls_label, _anchor(self.propagation), self, *feature_list)
 
 
 def load_pretrained(model, state_dict):

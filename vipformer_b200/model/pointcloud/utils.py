@@ -204,8 +204,19 @@ class _Group2EmbFn(torch.autograd.Function):
 
 
 class PointNetFeaturePropagation(nn.Module):
-    """utils.py:192-242 -- part-segmentation head; a later scope row, not built yet."""
+    """utils.py:192-242 -- parameter container (same `mlp_convs.i` / `mlp_bns.i` state_dict keys as the reference).  Its
+    arithmetic (3-NN inverse-distance interpolation + {Conv1d, BatchNorm1d, ReLU} stack) runs inside the fused part-segmentation
+    head of CrossFormer_partseg (vipformer_b200/functional_seg.py); calling the fragment on its own raises."""
 
     def __init__(self, in_channel, mlp):
         super().__init__()
-        raise NotImplementedError("PointNetFeaturePropagation (part segmentation) is not part of the pre-training hot path")
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last_channel = out_channel
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        _rt.fragment_error("PointNetFeaturePropagation")

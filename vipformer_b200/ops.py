@@ -353,3 +353,71 @@ def adamw(p, g, m, v, shadow, lr_ptr, step_ptr, beta1=0.9, beta2=0.999, eps=1e-8
 
 def step_advance(state):
     _lib.call("vpf_step_advance", _p(state), _s())
+
+
+# ----------------------------------------------------------------------------- part segmentation helpers
+def three_nn(pts, centers):
+    """pts fp32 [B,N,3], centers fp32 [B,S,3] -> (idx int32 [B,N,3], w fp32 [B,N,3])  (utils.py:223-229)."""
+    B, N, _ = pts.shape
+    S = centers.shape[1]
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=pts.device)
+    w = torch.empty((B, N, 3), dtype=F32, device=pts.device)
+    _lib.call("vpf_three_nn", _p(pts), _p(centers), _i(B), _i(N), _i(S), _p(idx), _p(w), _s())
+    return idx, w
+
+
+def interp3_fwd(feats, idx, w, pts, ldo):
+    """feats bf16 [B*S, C] -> bf16 [B*N, ldo]: columns [0,C) interpolated, [C,C+3) xyz, rest 0."""
+    B, N, _ = pts.shape
+    C = feats.shape[1]
+    S = feats.shape[0] // B
+    out = torch.empty((B * N, ldo), dtype=BF16, device=feats.device)
+    _lib.call("vpf_interp3_fwd", _p(feats), _i(feats.stride(0)), _p(idx), _p(w), _p(pts), _p(out), _i(ldo), _i(B), _i(N), _i(S),
+              _i(C), _s())
+    return out
+
+
+def interp3_bwd(dout, idx, w, dfeats, B, N, S, C):
+    _lib.call("vpf_interp3_bwd", _p(dout), _i(dout.stride(0)), _p(idx), _p(w), _p(dfeats), _i(dfeats.stride(0)), _i(B), _i(N),
+              _i(S), _i(C), _s())
+
+
+def token_pool_bf16_fwd(x, B, L, C):
+    out = torch.empty((B, 2 * C), dtype=F32, device=x.device)
+    am = torch.empty((B, C), dtype=torch.int32, device=x.device)
+    _lib.call("vpf_token_pool_bf16_fwd", _p(x), _i(x.stride(0)), _p(out), _p(am), _i(B), _i(L), _i(C), _s())
+    return out, am
+
+
+def token_pool_accum_bwd(dout, am, dx, B, L, C):
+    _lib.call("vpf_token_pool_accum_bwd", _p(dout), _p(am), _p(dx), _i(dx.stride(0)), _i(B), _i(L), _i(C), _s())
+
+
+def leaky_relu_fwd(x, slope):
+    y = torch.empty_like(x)
+    _lib.call("vpf_leaky_relu_fwd", _p(x), _p(y), _f(slope), _ll(x.numel()), _s())
+    return y
+
+
+def leaky_relu_bwd(dy, x, slope):
+    dx = torch.empty_like(x)
+    _lib.call("vpf_leaky_relu_bwd", _p(dy), _p(x), _p(dx), _f(slope), _ll(x.numel()), _s())
+    return dx
+
+
+def permute_w(W, C, ldo):
+    Co = W.shape[0]
+    out = torch.empty((Co, ldo), dtype=BF16, device=W.device)
+    _lib.call("vpf_permute_w", _p(W.contiguous()), _p(out), _i(Co), _i(C), _i(ldo), _s())
+    return out
+
+
+def unpermute_dw(dWp, dW, C):
+    _lib.call("vpf_unpermute_dw", _p(dWp), _p(dW), _i(dW.shape[0]), _i(C), _i(dWp.stride(0)), _s())
+
+
+def copy2d_bf16(src, dst):
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.dtype == BF16 and dst.dtype == BF16
+    _lib.call("vpf_copy2d_bf16", _p(src), _i(src.stride(0)), _p(dst), _i(dst.stride(0)), _ll(rows), _i(cols), _s())
+    return dst
