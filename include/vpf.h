@@ -280,6 +280,16 @@ int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc,
                    int n_c, int D, int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base,
                    float temperature, float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx,
                    void *stream);
+/* Packed form: nseg (<= 4) loss terms that share zc / lse_all in ONE launch per stage.  zr, norm, lse_out, dx, G_ws hold
+ * term t in rows [t * n_r, +n_r); S_ws is [nseg, n_r, n_c]; loss_out [nseg]; the column-map base of term t is
+ * zc_base + t * zc_base_stride; gscale is a HOST array [nseg]. */
+int vpf_ntxent_pack_fwd(const float *zr, int nseg, int n_r, const float *zc, int n_c, int D, int b_local,
+                        int col_offset, int half, int zc_blk, int zc_ld, int zc_base, int zc_base_stride,
+                        float temperature, float *S_ws, float *lse_out, float *loss_out, void *stream);
+int vpf_ntxent_pack_bwd(const float *zr, const float *norm, int nseg, int n_r, const float *zc,
+                        const float *lse_all, int n_c, int D, int b_local, int col_offset, int half, int zc_blk,
+                        int zc_ld, int zc_base, int zc_base_stride, float temperature, const float *gscale,
+                        const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream);
 /* nn.CrossEntropyLoss(label_smoothing = eps), mean reduction -- the fine-tune objective (ft_cls.py:145,176).
  * logits fp32 [n, ld] (C valid columns), labels int64 [n]; loss_out (+=, zero it first) and dlogits fp32 [n, ldd]
  * = d(mean loss)/d(logits), both produced in one pass. */
@@ -291,6 +301,17 @@ int vpf_adamw(float *p, const float *g, float *m, float *v, void *shadow_bf16, l
               const long long *step_ptr, float grad_scale, void *stream);
 /* state[0] += 1 (optimizer step), state[1] = next dropout seed. */
 int vpf_step_advance(long long *state, void *stream);
+/* n uniform indices in [0, N) drawn on the device from the step state's seed (state[1]) and a stream id: the FPS start
+ * points of utils.py:71 (torch.randint there) without a host round trip or a library RNG kernel inside the captured
+ * step.  out[i] = (hash(seed, op_id, i) * N) >> 32  -- restated in oracle/rng.py (draw_indices). */
+int vpf_draw_indices(const long long *state, unsigned int op_id, int n, int N, long long *out, void *stream);
+
+/* ---- scratch sizes (bytes) of the entries above that take caller-provided workspaces ---- */
+size_t vpf_attention_bwd_workspace_bytes(int B, int H, int Lq);           /* delta_ws            */
+size_t vpf_bn_bwd_workspace_bytes(int C);                                  /* red (vpf_bn_bwd)    */
+size_t vpf_linear3_bn_bwd_workspace_bytes(int Co);                         /* red                 */
+size_t vpf_ntxent_logits_workspace_bytes(int n_r, int n_c);                /* S_ws                */
+size_t vpf_ntxent_grad_workspace_bytes(int n_r, int D);                    /* G_ws                */
 
 #ifdef __cplusplus
 }

@@ -61,3 +61,11 @@ def attention_keep(seed, op_id, p, BH, Lq, Lk):
     byte = (h >> ((j & np.uint64(3)) * np.uint64(8))) & np.uint64(0xFF)
     keep = byte >= np.uint64(thr)
     return keep.astype(np.float32) * np.float32(256.0 / (256.0 - thr))
+
+
+def draw_indices(seed, op_id, n, N):
+    """vpf_draw_indices (augment.cu): n indices in [0, N) from (seed, op_id): (hash * N) >> 32.  int64 array."""
+    key = np.uint64(make_key(seed, op_id))
+    i = np.arange(n, dtype=np.uint64)
+    h = mix32(((i * np.uint64(0x9E3779B1)) & _M) ^ key)
+    return ((h * np.uint64(N)) >> np.uint64(32)).astype(np.int64)

@@ -59,3 +59,19 @@ def test_augmented_views_feed_the_tokenizer():
     onb, oce, ofi, oki = T.divide_patches(view.cpu().numpy(), 96, 32, start.cpu().numpy(), return_indices=True)
     assert np.array_equal(fi.cpu().numpy(), ofi) and np.array_equal(ki.cpu().numpy(), oki)
     assert np.array_equal(nb.cpu().numpy(), onb) and np.array_equal(ce.cpu().numpy(), oce)
+
+
+@pytest.mark.parametrize("n,N", [(512, 2048), (7, 1), (1000, 1024), (33, 333)])
+def test_draw_indices_bit_exact_vs_oracle(n, N):
+    """FPS start points of the engine step (utils.py:71 draws them with torch.randint): integer work, bit-exact."""
+    import oracle.rng as R
+    from vipformer_b200 import ops
+
+    state = torch.tensor([3, 0x1234567890ABCDEF - (1 << 63)], dtype=torch.int64, device="cuda")
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    ops.draw_indices(state, 0xF9500000, N, out)
+    ref = R.draw_indices(int(state[1].item()) & 0xFFFFFFFFFFFFFFFF, 0xF9500000, n, N)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert int(out.min()) >= 0 and int(out.max()) < N
+    if n >= 512:      # roughly uniform: every quarter of the range is hit
+        assert len(set((out.cpu().numpy() * 4 // N).tolist())) == 4

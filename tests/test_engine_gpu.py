@@ -173,7 +173,11 @@ def test_engine_step_matches_oracle_fwd_bwd_adamw():
         big = g.reshape(-1).abs() > 0.05 * g.abs().mean()
         agree_n += int((torch.sign(d_eng[big]) == torch.sign(d_ref[big])).sum())
         agree_d += int(big.sum())
-        cos = torch.nn.functional.cosine_similarity(d_eng.double().view(1, -1), d_ref.double().view(1, -1)).item()
+        # AdamW's first step is lr * sign(g) per element: elements whose gradient is noise-sized carry a random sign on
+        # both sides, so the direction is compared on the elements with a gradient worth the name (the same `big` mask)
+        if int(big.sum()) < 8:
+            continue
+        cos = torch.nn.functional.cosine_similarity(d_eng[big].double().view(1, -1), d_ref[big].double().view(1, -1)).item()
         if cos < 0.93:
             bad.append((n, "delta cos", round(cos, 4)))
     assert not bad, bad

@@ -198,3 +198,15 @@ def test_partseg_oracle_matches_reference(name, golden_dir):
         if key.startswith("buf::"):
             k = key.split("::")[1]
             assert _rel(o["run"][k], g[key]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", ["seg_small", "seg_cfgA"])
+def test_partseg_mirror_parameter_names_match_reference(name, golden_dir):
+    """The mirror's trainable parameters carry the reference's names (the fixture lists the real model's named_parameters
+    that received a gradient), so its checkpoints load both ways (ft_partseg.py:96-104)."""
+    cfg = _synth.SEG_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    mine = {k for k, p in _synth.build_seg_model(cfg).named_parameters()}
+    assert set(map(str, g["grad_names"])) <= mine
+    # parameters of the reference without a gradient: biases nothing (all used); the mirror has no extra trainables
+    assert {k for k in mine if k not in set(map(str, g["grad_names"]))} == set()

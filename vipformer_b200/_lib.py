@@ -27,8 +27,6 @@ def lib():
         _lib.vpf_last_error_string.restype = ctypes.c_char_p
         _lib.vpf_launch_count.restype = ctypes.c_int64
         _lib.vpf_abi_version.restype = ctypes.c_int
-        for name in dir(_lib):
-            pass
     return _lib
 
 

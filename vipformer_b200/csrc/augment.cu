@@ -8,6 +8,7 @@
 // (oracle/augment.py, pinned to the reference classes) can check on identical draws.
 // One CTA per cloud; the cloud lives in shared memory; three block reductions (centroid, radius, bounding box).
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace vpf {
 
@@ -108,9 +109,31 @@ augment_kernel(const float *__restrict__ pts, const float *__restrict__ params, 
   }
 }
 
+// FPS start indices (utils.py:71): out[i] = floor(u * N), u = 32-bit hash of (seed, op_id, i) / 2^32
+__global__ void draw_indices_kernel(const long long *__restrict__ state, uint32_t op_id, int n, int N, long long *__restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t key = rng::make_key((unsigned long long)state[1], op_id);
+  const uint32_t h = rng::mix32((uint32_t)i * 0x9e3779b1u ^ key);
+  out[i] = (long long)(((unsigned long long)h * (unsigned long long)N) >> 32);
+}
+
 }  // namespace vpf
 
 using namespace vpf;
+
+extern "C" int vpf_draw_indices(const long long *state, unsigned int op_id, int n, int N, long long *out, void *stream) {
+  VPF_REQUIRE(state && out && N >= 1, "draw_indices: bad arguments (N=%d)", N);
+  if (n == 0) return VPF_OK;
+  draw_indices_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(state, op_id, n, N, out);
+  return check_launch("draw_indices_kernel");
+}
+
+extern "C" size_t vpf_attention_bwd_workspace_bytes(int B, int H, int Lq) { return (size_t)B * H * Lq * sizeof(float); }
+extern "C" size_t vpf_bn_bwd_workspace_bytes(int C) { return (size_t)3 * C * sizeof(double); }
+extern "C" size_t vpf_linear3_bn_bwd_workspace_bytes(int Co) { return (size_t)2 * Co * sizeof(double); }
+extern "C" size_t vpf_ntxent_logits_workspace_bytes(int n_r, int n_c) { return (size_t)n_r * n_c * sizeof(float); }
+extern "C" size_t vpf_ntxent_grad_workspace_bytes(int n_r, int D) { return (size_t)n_r * D * sizeof(float); }
 
 extern "C" int vpf_augment_clouds(const float *pts, const float *params, const float *jitter, const float *drop_u, float *out,
                                   int B, int N, float jitter_clip, void *stream) {

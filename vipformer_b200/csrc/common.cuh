@@ -57,4 +57,21 @@ inline int num_sms() {
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// Resident CTAs of `kernel` on the whole device (SMs x occupancy): the grid of a streaming kernel that strides over its
+// rows.  A grid a little larger than this runs a second, mostly empty wave -- at 591 CTAs over 444 slots the LayerNorm
+// backward lost a third of its bandwidth to that tail.  One occupancy query per (kernel, block, smem) call site.
+template <typename K>
+inline int resident_ctas(K kernel, int threads, size_t dyn_smem = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  return num_sms() * per_sm;
+}
+#define VPF_RESIDENT_CTAS(var, kernel, threads, smem)              \
+  static int var##_cached = 0;                                      \
+  if (var##_cached == 0) var##_cached = ::vpf::resident_ctas(kernel, threads, smem); \
+  const int var = var##_cached
+
 }  // namespace vpf

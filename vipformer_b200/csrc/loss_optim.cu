@@ -46,8 +46,12 @@ __device__ __forceinline__ void self_pos(int i, int b_local, int col_offset, int
 constexpr int kSgTile = 64, kSgK = 64;   // K slab of 64: 4x fewer load -> sync -> FMA -> sync rounds than 16 (the kernel is latency bound: 32-64 CTAs)
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K,
-             float alpha, int b_nt, ColMap cm) {   // cm maps the logits-column index (n if b_nt, else k) to a row of B
+             float alpha, int b_nt, ColMap cm, int cm_base_stride) {   // cm maps the logits-column index (n if b_nt, else k) to a row of B
   __shared__ float sA[kSgK][kSgTile + 4], sB[kSgK][kSgTile + 4];
+  // blockIdx.z = loss term of a packed call: its own A rows, C block and column-map base; B (all gathered rows) is shared
+  A += (size_t)blockIdx.z * M * K;
+  C += (size_t)blockIdx.z * M * N;
+  cm.base += (int)blockIdx.z * cm_base_stride;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * kSgTile, n0 = blockIdx.x * kSgTile;
   float acc[4][4];
@@ -103,6 +107,9 @@ ntxent_rowlse_kernel(const float *__restrict__ S, int n_r, int n_c, int b_local,
                      float *__restrict__ lse_out, float *__restrict__ loss_out) {
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n_r) return;
+  S += (size_t)blockIdx.y * n_r * n_c;      // blockIdx.y = loss term of a packed call
+  lse_out += (size_t)blockIdx.y * n_r;
+  loss_out += blockIdx.y;
   int self, pos;
   self_pos(i, b_local, col_offset, half, self, pos);
   const float *row = S + (size_t)i * n_c;
@@ -123,8 +130,10 @@ ntxent_rowlse_kernel(const float *__restrict__ S, int n_r, int n_c, int b_local,
 // in place: S[k,j] <- w_kj = [j != self(k)] (exp(s - lse_k) + exp(s - lse_all[j])) - 2 [j == pos(k)]
 __global__ void __launch_bounds__(256)
 ntxent_weights_kernel(float *__restrict__ S, const float *__restrict__ lse_all, int n_r, int n_c, int b_local,
-                      int col_offset, int half, ColMap cm) {
+                      int col_offset, int half, ColMap cm, int cm_base_stride) {
   const size_t total = (size_t)n_r * n_c;
+  S += (size_t)blockIdx.y * total;          // blockIdx.y = loss term of a packed call
+  cm.base += (int)blockIdx.y * cm_base_stride;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
     const int k = (int)(e / n_c), j = (int)(e % n_c);
     int self, pos;
@@ -138,12 +147,13 @@ ntxent_weights_kernel(float *__restrict__ S, const float *__restrict__ lse_all, 
 }
 
 // dx_k = (g_k - z_k (z_k . g_k)) / norm_k with g_k = sc * G[k,:]   (backward of F.normalize); one warp per row
+struct SegScale { float v[4]; };
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float *__restrict__ G, const float *__restrict__ z, const float *__restrict__ norm,
-                  float sc, const float *__restrict__ upstream, float *__restrict__ dx, int n, int D) {
+                  SegScale sc, int seg_rows, const float *__restrict__ upstream, float *__restrict__ dx, int n, int D) {
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (k >= n) return;
-  const float s = sc * (upstream ? upstream[0] : 1.f);
+  const float s = sc.v[k / seg_rows] * (upstream ? upstream[0] : 1.f);   // rows [t * seg_rows, +seg_rows) belong to loss term t
   float zg = 0.f;
   for (int d = lane; d < D; d += 32) zg += z[(size_t)k * D + d] * G[(size_t)k * D + d] * s;
   zg = wsum(zg);
@@ -231,35 +241,58 @@ static int check_cols(const char *what, int n_r, int n_c, int b_local, int col_o
   return VPF_OK;
 }
 
-int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local, int col_offset, int half,
-                   int zc_blk, int zc_ld, int zc_base, float temperature, float *S_ws, float *lse_out, float *loss_out,
-                   void *stream) {
+// Packed form: nseg (<= 4) loss terms in ONE launch per stage.  zr [nseg * n_r, D] (term t = rows [t n_r, +n_r)), S_ws
+// [nseg, n_r, n_c], lse_out [nseg * n_r], loss_out [nseg]; the column map base of term t is zc_base + t * zc_base_stride.
+int vpf_ntxent_pack_fwd(const float *zr, int nseg, int n_r, const float *zc, int n_c, int D, int b_local, int col_offset,
+                        int half, int zc_blk, int zc_ld, int zc_base, int zc_base_stride, float temperature, float *S_ws,
+                        float *lse_out, float *loss_out, void *stream) {
   VPF_REQUIRE(zr && zc && S_ws && lse_out && loss_out, "ntxent_fwd: null pointer");
+  VPF_REQUIRE(nseg >= 1 && nseg <= 4, "ntxent_fwd: nseg=%d out of range (1..4)", nseg);
   VPF_TRY(check_cols("ntxent_fwd", n_r, n_c, b_local, col_offset, half, temperature, zc_blk, zc_ld));
   if (n_r == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const ColMap cm{zc_blk, zc_ld, zc_base};
-  sgemm_kernel<<<dim3(ceil_div(n_c, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(zr, zc, S_ws, n_r, n_c, D, 1.f / temperature, 1, cm);
+  sgemm_kernel<<<dim3(ceil_div(n_c, kSgTile), ceil_div(n_r, kSgTile), nseg), 256, 0, st>>>(zr, zc, S_ws, n_r, n_c, D, 1.f / temperature, 1, cm, zc_base_stride);
   VPF_TRY(check_launch("sgemm_kernel"));
-  ntxent_rowlse_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(S_ws, n_r, n_c, b_local, col_offset, half, lse_out, loss_out);
+  ntxent_rowlse_kernel<<<dim3(ceil_div(n_r, 8), nseg), 256, 0, st>>>(S_ws, n_r, n_c, b_local, col_offset, half, lse_out, loss_out);
   return check_launch("ntxent_rowlse_kernel");
 }
 
-int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all, int n_c, int D,
-                   int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base, float temperature,
-                   float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream) {
-  VPF_REQUIRE(zr && norm && zc && lse_all && S_ws && G_ws && dx, "ntxent_bwd: null pointer");
+int vpf_ntxent_fwd(const float *zr, int n_r, const float *zc, int n_c, int D, int b_local, int col_offset, int half,
+                   int zc_blk, int zc_ld, int zc_base, float temperature, float *S_ws, float *lse_out, float *loss_out,
+                   void *stream) {
+  return vpf_ntxent_pack_fwd(zr, 1, n_r, zc, n_c, D, b_local, col_offset, half, zc_blk, zc_ld, zc_base, 0, temperature, S_ws,
+                             lse_out, loss_out, stream);
+}
+
+// gscale [nseg] (host array): per-term seed of the gradient; dx [nseg * n_r, D]; G_ws [nseg * n_r, D]
+int vpf_ntxent_pack_bwd(const float *zr, const float *norm, int nseg, int n_r, const float *zc, const float *lse_all, int n_c,
+                        int D, int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base, int zc_base_stride,
+                        float temperature, const float *gscale, const float *upstream, float *S_ws, float *G_ws, float *dx,
+                        void *stream) {
+  VPF_REQUIRE(zr && norm && zc && lse_all && S_ws && G_ws && dx && gscale, "ntxent_bwd: null pointer");
+  VPF_REQUIRE(nseg >= 1 && nseg <= 4, "ntxent_bwd: nseg=%d out of range (1..4)", nseg);
   VPF_TRY(check_cols("ntxent_bwd", n_r, n_c, b_local, col_offset, half, temperature, zc_blk, zc_ld));
   if (n_r == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)n_r * n_c;
   const ColMap cm{zc_blk, zc_ld, zc_base};
-  ntxent_weights_kernel<<<(int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)), 256, 0, st>>>(S_ws, lse_all, n_r, n_c, b_local, col_offset, half, cm);
+  const int wgrid = (int)min((size_t)max(1, num_sms() * 8 / nseg), ceil_div(total, (size_t)256));
+  ntxent_weights_kernel<<<dim3(wgrid, nseg), 256, 0, st>>>(S_ws, lse_all, n_r, n_c, b_local, col_offset, half, cm, zc_base_stride);
   VPF_TRY(check_launch("ntxent_weights_kernel"));
-  sgemm_kernel<<<dim3(ceil_div(D, kSgTile), ceil_div(n_r, kSgTile)), 256, 0, st>>>(S_ws, zc, G_ws, n_r, D, n_c, 1.f, 0, cm);
+  sgemm_kernel<<<dim3(ceil_div(D, kSgTile), ceil_div(n_r, kSgTile), nseg), 256, 0, st>>>(S_ws, zc, G_ws, n_r, D, n_c, 1.f, 0, cm, zc_base_stride);
   VPF_TRY(check_launch("sgemm_kernel"));
-  l2norm_bwd_kernel<<<ceil_div(n_r, 8), 256, 0, st>>>(G_ws, zr, norm, gscale / temperature, upstream, dx, n_r, D);
+  SegScale sc;
+  for (int t = 0; t < 4; ++t) sc.v[t] = t < nseg ? gscale[t] / temperature : 0.f;
+  l2norm_bwd_kernel<<<ceil_div(nseg * n_r, 8), 256, 0, st>>>(G_ws, zr, norm, sc, n_r, upstream, dx, nseg * n_r, D);
   return check_launch("l2norm_bwd_kernel");
+}
+
+int vpf_ntxent_bwd(const float *zr, const float *norm, int n_r, const float *zc, const float *lse_all, int n_c, int D,
+                   int b_local, int col_offset, int half, int zc_blk, int zc_ld, int zc_base, float temperature,
+                   float gscale, const float *upstream, float *S_ws, float *G_ws, float *dx, void *stream) {
+  return vpf_ntxent_pack_bwd(zr, norm, 1, n_r, zc, lse_all, n_c, D, b_local, col_offset, half, zc_blk, zc_ld, zc_base, 0,
+                             temperature, &gscale, upstream, S_ws, G_ws, dx, stream);
 }
 
 int vpf_ce_ls(const float *logits, int ld, const long long *labels, int n, int C, float eps, float *loss_out,

@@ -42,17 +42,14 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p,
 }
 
 // ------------------------------------------------------------- LayerNorm fwd
-// one warp per row; NPER = D/32 values per lane held in registers.  VEC: lane owns float4 groups (D % 128 == 0).
+// One warp per row, NPER = D/32 values per lane held in registers.  VEC: lane owns float4 groups (D % 128 == 0).
+// The grid is the resident set (SMs x occupancy) and every warp strides over the rows with the NEXT row's loads issued
+// before the current row is reduced and stored: two rows of loads in flight per warp, no CTA turnover
+// (the 8-rows-per-CTA version ran at 60 % of the HBM copy rate).
 template <typename Tin, int NPER, bool VEC>
-__global__ void __launch_bounds__(256)
-ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
-              const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
-              float *__restrict__ mean_out, float *__restrict__ rstd_out, int T, float eps, int relu) {
+__device__ __forceinline__ void ln_load_row(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, int row,
+                                            int lane, float (&v)[NPER]) {
   constexpr int D = NPER * 32;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= T) return;
-  float v[NPER];
-  float s = 0.f;
   if constexpr (VEC) {
 #pragma unroll
     for (int q = 0; q < NPER / 4; ++q) {
@@ -63,8 +60,6 @@ ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_
         t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
       }
       v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-      s += (t.x + t.y) + (t.z + t.w);
-      if (xsum) st4<float>(xsum, (size_t)row * D + c, t);
     }
   } else {
 #pragma unroll
@@ -73,34 +68,60 @@ ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_
       float t = ldf<Tin>(x, (size_t)row * D + c);
       if (add) t += add[(size_t)(row % add_rows) * D + c];
       v[i] = t;
-      s += t;
-      if (xsum) xsum[(size_t)row * D + c] = t;
     }
   }
-  const float mean = warp_sum(s) * (1.f / D);
-  float q2 = 0.f;
+}
+
+template <typename Tin, int NPER, bool VEC>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
+              const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
+              float *__restrict__ mean_out, float *__restrict__ rstd_out, int T, float eps, int relu) {
+  constexpr int D = NPER * 32;
+  const int lane = threadIdx.x & 31, nwarps = gridDim.x * 8;
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= T) return;
+  auto col = [&](int i) { return VEC ? (lane + 32 * (i >> 2)) * 4 + (i & 3) : lane + 32 * i; };
+  float gm[NPER], bt[NPER];
 #pragma unroll
-  for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q2 += d * d; }
-  const float rstd = rsqrtf(warp_sum(q2) * (1.f / D) + eps);
-  if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
-  if constexpr (VEC) {
+  for (int i = 0; i < NPER; ++i) { gm[i] = gamma[col(i)]; bt[i] = beta[col(i)]; }
+  float v[NPER], vn[NPER];
+  ln_load_row<Tin, NPER, VEC>(x, add, add_rows, row, lane, v);
+  for (; row < T; row += nwarps) {
+    const int next = row + nwarps;
+    if (next < T) ln_load_row<Tin, NPER, VEC>(x, add, add_rows, next, lane, vn);
+    float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < NPER / 4; ++q) {
-      const int c = (lane + 32 * q) * 4;
-      const float4 g = ld4<float>(gamma, c), b = ld4<float>(beta, c);
-      float4 o = make_float4((v[4 * q] - mean) * rstd * g.x + b.x, (v[4 * q + 1] - mean) * rstd * g.y + b.y,
-                             (v[4 * q + 2] - mean) * rstd * g.z + b.z, (v[4 * q + 3] - mean) * rstd * g.w + b.w);
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      st4<__nv_bfloat16>(y, (size_t)row * D + c, o);
-    }
-  } else {
+    for (int i = 0; i < NPER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / D);
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q2 += d * d; }
+    const float rstd = rsqrtf(warp_sum(q2) * (1.f / D) + eps);
+    if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
+    float o[NPER];
 #pragma unroll
     for (int i = 0; i < NPER; ++i) {
-      const int c = lane + 32 * i;
-      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-      if (relu) o = fmaxf(o, 0.f);
-      y[(size_t)row * D + c] = __float2bfloat16(o);
+      o[i] = (v[i] - mean) * rstd * gm[i] + bt[i];
+      if (relu) o[i] = fmaxf(o[i], 0.f);
     }
+    if constexpr (VEC) {
+#pragma unroll
+      for (int q = 0; q < NPER / 4; ++q) {
+        const size_t e = (size_t)row * D + (lane + 32 * q) * 4;
+        if (xsum) st4<float>(xsum, e, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        st4<__nv_bfloat16>(y, e, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const size_t e = (size_t)row * D + lane + 32 * i;
+        if (xsum) xsum[e] = v[i];
+        y[e] = __float2bfloat16(o[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) v[i] = vn[i];
   }
 }
 
@@ -634,12 +655,21 @@ colreduce_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *
 // MUFU/FMA latency chains that a 16-warp GEMM epilogue cannot.
 __global__ void __launch_bounds__(256)
 gelu_fwd_kernel(const uint4 *__restrict__ z, uint4 *__restrict__ h, size_t n8) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
-    float f[8];
-    unpack8(__ldg(z + i), f);
+  constexpr int U = 4;      // 4 independent 16-byte loads per thread before the first use (64 B in flight per thread)
+  for (size_t i0 = (size_t)blockIdx.x * (256 * U) + threadIdx.x; i0 < n8; i0 += (size_t)gridDim.x * (256 * U)) {
+    uint4 u[U];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) f[q] = gelu_f(f[q]);
-    h[i] = pack8(f);
+    for (int k = 0; k < U; ++k)
+      if (i0 + (size_t)k * 256 < n8) u[k] = __ldg(z + i0 + (size_t)k * 256);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (i0 + (size_t)k * 256 >= n8) continue;
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = gelu_f(f[q]);
+      h[i0 + (size_t)k * 256] = pack8(f);
+    }
   }
 }
 
@@ -700,9 +730,9 @@ __global__ void bn_bwd_means_kernel(const double *__restrict__ red, float *__res
   if (dgamma) { dgamma[c] += (float)red[C + c]; dbeta[c] += (float)red[c]; }
 }
 
-static inline void bf16_col_cfg(long long R, int C, dim3 &grid, int &rows_per_cta, int &smem) {
+static inline void bf16_col_cfg(long long R, int C, dim3 &grid, int &rows_per_cta, int &smem, int slots = 0) {
   const int cg = C / 8, cgx = min(cg, 256), ny = 256 / cgx, gy = ceil_div(cg, cgx);
-  const long long want_ctas = max(1, num_sms() * 6 / gy);
+  const long long want_ctas = max(1, (slots > 0 ? slots : num_sms() * 6) / gy);
   rows_per_cta = (int)max((long long)ny * 8, ceil_div(R, want_ctas));
   grid = dim3((unsigned)ceil_div(R, (long long)rows_per_cta), gy);
   smem = 2 * ny * cgx * 8 * (int)sizeof(float);   // colreduce: one slot per thread and statistic
@@ -736,12 +766,18 @@ int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows,
   VPF_REQUIRE(!add || add_rows > 0, "layernorm_fwd: add_rows must be > 0");
   if (T == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ceil_div(T, 8);
-#define LNF(NP, VEC)                                                                                                \
-  if (x_bf16) ln_fwd_kernel<bf16, NP, VEC><<<grid, 256, 0, st>>>((const bf16 *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
-  else ln_fwd_kernel<float, NP, VEC><<<grid, 256, 0, st>>>((const float *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu)
+#define LNF_CALL(TIN, NP, VEC)                                                                                      \
+  {                                                                                                                 \
+    VPF_RESIDENT_CTAS(slots, (ln_fwd_kernel<TIN, NP, VEC>), 256, 0);                                                 \
+    const int grid = min(ceil_div(T, 8), slots);                                                                    \
+    ln_fwd_kernel<TIN, NP, VEC><<<grid, 256, 0, st>>>((const TIN *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
+  }
+#define LNF(NP, VEC)                          \
+  if (x_bf16) LNF_CALL(bf16, NP, VEC)         \
+  else LNF_CALL(float, NP, VEC)
   LN_DISPATCH(D, LNF)
 #undef LNF
+#undef LNF_CALL
   return check_launch("ln_fwd_kernel");
 }
 
@@ -752,24 +788,29 @@ int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, co
   VPF_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be given or both null");
   if (T == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int rows_per_cta = max(8, ceil_div(T, num_sms() * 4));
-  int grid = ceil_div(T, rows_per_cta);
-  if (dpos && pos_rows < T) {
-    // token-major order (see the kernel): warps = pos_rows * nchunk, every (token, batch-chunk) pair one warp
-    VPF_REQUIRE(pos_rows > 0 && T % pos_rows == 0, "layernorm_bwd: T=%d is not a multiple of pos_rows=%d", T, pos_rows);
-    const int batch = T / pos_rows;
-    const int nchunk = max(1, min(batch, (num_sms() * 4 * 8) / pos_rows));
-    grid = ceil_div(pos_rows * nchunk, 8);
-  }
+  const bool tok_major = dpos && pos_rows < T;
+  if (tok_major) VPF_REQUIRE(pos_rows > 0 && T % pos_rows == 0, "layernorm_bwd: T=%d is not a multiple of pos_rows=%d", T, pos_rows);
+  // grid = the resident set (a partial second wave cost a third of the bandwidth).  Token-major order (see the kernel):
+  // warps = pos_rows * nchunk, every (token, batch-chunk) pair one warp
 #define LNB_CALL(TDY, TX, TDX, NP, VEC)                                                                               \
-  ln_bwd_kernel<TDY, TX, TDX, NP, VEC><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
-                                                         (TDX *)dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta)
+  {                                                                                                                   \
+    VPF_RESIDENT_CTAS(slots, (ln_bwd_kernel<TDY, TX, TDX, NP, VEC>), 256, 0);                                          \
+    int grid = min(ceil_div(T, 8), slots);                                                                            \
+    const int rows_per_cta = ceil_div(T, grid);                                                                       \
+    grid = ceil_div(T, rows_per_cta);                                                                                 \
+    if (tok_major) {                                                                                                  \
+      const int nchunk = max(1, min(T / pos_rows, (slots * 8) / pos_rows));                                           \
+      grid = ceil_div(pos_rows * nchunk, 8);                                                                          \
+    }                                                                                                                 \
+    ln_bwd_kernel<TDY, TX, TDX, NP, VEC><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
+                                                           (TDX *)dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta); \
+  }
 #define LNB(NP, VEC)                                                                     \
-  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP, VEC);                 \
-  else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP, VEC);          \
-  else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP, VEC);      \
-  else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP, VEC);        \
-  else if (dy_bf16 && x_bf16 && !dx_bf16) LNB_CALL(bf16, bf16, float, NP, VEC);          \
+  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP, VEC)                  \
+  else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP, VEC)           \
+  else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP, VEC)       \
+  else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP, VEC)         \
+  else if (dy_bf16 && x_bf16 && !dx_bf16) LNB_CALL(bf16, bf16, float, NP, VEC)           \
   else return fail(VPF_EINVAL, "layernorm_bwd: unsupported dtype combination dy_bf16=%d x_bf16=%d dx_bf16=%d", dy_bf16, x_bf16, dx_bf16)
   LN_DISPATCH(D, LNB)
 #undef LNB
@@ -783,7 +824,8 @@ int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p, con
   VPF_REQUIRE(p >= 0.f && p < 1.f, "dropout_grad: p=%f out of range", p);
   VPF_REQUIRE((size_t)T * (size_t)N < (1ull << 32), "dropout_grad: index space exceeds 2^32");
   if (T == 0 || N == 0) return VPF_OK;
-  const int rows_per_cta = max(1, ceil_div(T, num_sms() * 8));
+  VPF_RESIDENT_CTAS(slots, dropout_grad_vec_kernel<4>, 256, 0);
+  const int rows_per_cta = max(1, ceil_div(T, slots));
   const int lanes = N / 4;
   if (N % 4 == 0 && lanes <= 256 && 256 % lanes == 0 && (256 / lanes) * N <= 1024 &&
       ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0) {
@@ -810,6 +852,8 @@ int vpf_colsum(const void *x, int x_bf16, double *sum, double *sumsq, float *sum
   if (x_bf16 && C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     dim3 g8; int rpc, smem;
     bf16_col_cfg(R, C, g8, rpc, smem);
+    VPF_RESIDENT_CTAS(slots, colreduce_bf16_kernel<0>, 256, (size_t)smem);
+    bf16_col_cfg(R, C, g8, rpc, smem, slots);
     colreduce_bf16_kernel<0><<<g8, 256, smem, (cudaStream_t)stream>>>((const bf16 *)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sum, sumsq, sum_f32, R, C, rpc);
     return check_launch("colreduce_bf16_kernel<0>");
   }
@@ -839,7 +883,8 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
   const int grid = grid_for(total);
   if (x_bf16 && y_bf16 && C % 8 == 0) {
     dim3 g8; int rpc, smem;
-    bf16_col_cfg(R, C, g8, rpc, smem);
+    VPF_RESIDENT_CTAS(slots, bn_apply_bf16_kernel, 256, 0);
+    bf16_col_cfg(R, C, g8, rpc, smem, slots);
     bn_apply_bf16_kernel<<<g8, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, R, C, rpc);
   }
   else if (x_bf16 && y_bf16) bn_apply_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x, scale, shift, (bf16 *)y, relu, total, C);
@@ -870,11 +915,15 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
   if (dy_bf16 && x_bf16 && dx_bf16 && C % 8 == 0) {
     dim3 g8; int rpc, smem;
     bf16_col_cfg(R, C, g8, rpc, smem);
+    VPF_RESIDENT_CTAS(slots, colreduce_bf16_kernel<1>, 256, (size_t)smem);
+    bf16_col_cfg(R, C, g8, rpc, smem, slots);
     colreduce_bf16_kernel<1><<<g8, 256, smem, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, red, red + C, nullptr, R, C, rpc);
     VPF_TRY(check_launch("colreduce_bf16_kernel<1>"));
     float *fm = reinterpret_cast<float *>(red + 2 * C);   // caller provides 3C doubles of scratch
     bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, fm, dgamma, dbeta, R, C);
     VPF_TRY(check_launch("bn_bwd_means_kernel"));
+    VPF_RESIDENT_CTAS(slots2, bn_bwd_apply_bf16_kernel, 256, 0);
+    bf16_col_cfg(R, C, g8, rpc, smem, slots2);
     bn_bwd_apply_bf16_kernel<<<g8, 256, 0, st>>>((const bf16 *)dy, (const bf16 *)x, scale, shift, mean, rstd, relu, fm, (bf16 *)dx, R, C, rpc);
   } else
   if (dy_bf16 && x_bf16 && dx_bf16) BNB(bf16, bf16, bf16)
@@ -892,7 +941,9 @@ int vpf_gelu_fwd(const void *z_bf16, void *h_bf16, long long n, void *stream) {
   VPF_REQUIRE(z_bf16 && h_bf16, "gelu_fwd: null pointer");
   VPF_REQUIRE(n % 8 == 0, "gelu_fwd: n=%lld must be a multiple of 8", n);
   if (n == 0) return VPF_OK;
-  gelu_fwd_kernel<<<grid_for((size_t)n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4 *)z_bf16, (uint4 *)h_bf16, (size_t)n / 8);
+  VPF_RESIDENT_CTAS(slots, gelu_fwd_kernel, 256, 0);
+  const int grid = (int)min((size_t)slots, ceil_div((size_t)n / 8, (size_t)1024));
+  gelu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)z_bf16, (uint4 *)h_bf16, (size_t)n / 8);
   return check_launch("gelu_fwd_kernel");
 }
 
@@ -901,7 +952,9 @@ int vpf_gelu_bwd(const void *dh_bf16, const void *z_bf16, void *dz_bf16, float *
   VPF_REQUIRE(C % 8 == 0, "gelu_bwd: C=%d must be a multiple of 8", C);
   if (R == 0 || C == 0) return VPF_OK;
   dim3 g8; int rpc, smem;
-  bf16_col_cfg(R, C, g8, rpc, smem);
+  smem = min(C / 8, 256) * 8 * (int)sizeof(float);
+  VPF_RESIDENT_CTAS(slots, gelu_bwd_kernel, 256, smem);
+  bf16_col_cfg(R, C, g8, rpc, smem, slots);
   smem = min(C / 8, 256) * 8 * (int)sizeof(float);
   gelu_bwd_kernel<<<g8, 256, smem, (cudaStream_t)stream>>>((const bf16 *)dh_bf16, (const bf16 *)z_bf16, (bf16 *)dz_bf16, colsum, R, C, rpc);
   return check_launch("gelu_bwd_kernel");

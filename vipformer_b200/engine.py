@@ -18,6 +18,8 @@ import torch.nn as nn
 from . import ops, params, runtime
 from .loss import pretrain_loss
 
+FPS_START_OP = 0xF9500000   # stream id of the per-step FPS start draw (ops.draw_indices); dropout sites use small ids
+
 F32 = torch.float32
 
 
@@ -83,8 +85,6 @@ class PretrainEngine:
         self.start = torch.zeros(2 * b, dtype=torch.long, device=self.device)
         self.losses = torch.zeros(3, dtype=F32, device=self.device)
         self.losses_host = torch.zeros(3, dtype=F32).pin_memory()
-        self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(1234 + self.rank)
         self.use_graph = use_cuda_graph
         self.graph = None
         self.side = torch.cuda.Stream(device=self.device) if overlap_branches else None
@@ -99,8 +99,8 @@ class PretrainEngine:
     def _step_body(self):
         ops.step_advance(self.state)                      # step += 1, fresh dropout seed
         self.arena.zero_grads()                           # optimizer.zero_grad (pretrain.py:174)
-        torch.randint(0, self.N, (2 * self.b,), dtype=torch.long, device=self.device, generator=self.gen, out=self.start)
-        self.pc_model.fps_start_idx = self.start          # utils.py:71, drawn on the device
+        ops.draw_indices(self.state, FPS_START_OP, self.N, self.start)   # utils.py:71, drawn on the device from the step seed
+        self.pc_model.fps_start_idx = self.start
         imgs = self.img_in.permute(0, 2, 3, 1) if self.images_nchw else self.img_in   # pretrain.py:179
         if self.side is not None:
             # the two encoders are independent until the loss: the image branch runs on a second stream so that its
@@ -129,15 +129,14 @@ class PretrainEngine:
         """Everything a step mutates besides the activations: parameters, Adam moments, step/seed state, BatchNorm
         buffers, the FPS-start generator."""
         return ([t.clone() for t in (self.arena.flat_p, self.arena.flat_bf, self.m, self.v, self.state)],
-                [b.clone() for b in self.root.buffers()], self.gen.get_state())
+                [b.clone() for b in self.root.buffers()])
 
     def _restore(self, snap):
-        tensors, bufs, gstate = snap
+        tensors, bufs = snap
         for dst, src in zip((self.arena.flat_p, self.arena.flat_bf, self.m, self.v, self.state), tensors):
             dst.copy_(src)
         for dst, src in zip(self.root.buffers(), bufs):
             dst.copy_(src)
-        self.gen.set_state(gstate)
 
     def _capture(self):
         # Warm-up outside capture (allocator pools, lazy module init, NCCL) must not train: the reference takes exactly
@@ -153,11 +152,6 @@ class PretrainEngine:
         self._restore(snap)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.gen_state_registered = False
-        try:
-            self.graph.register_generator_state(self.gen)
-        except Exception:
-            pass
         with torch.cuda.graph(self.graph):
             self._step_body()
 

@@ -66,20 +66,15 @@ class _NTXentPack:
             zc = z
         col_offset, half = shard_layout(r, W, b)
         n_c = W * n_r
-        losses = ops.zeros_(torch.empty(nseg, dtype=F32, device=dev))
-        lse = torch.empty(n, dtype=F32, device=dev)
-        S = []
-        for s in range(nseg):
-            cm = (n_r, n, s * n_r)
-            _, Ss = ops.ntxent_fwd(z[s * n_r:(s + 1) * n_r], zc, b, col_offset, half, temperature, losses[s:s + 1],
-                                   n_c=n_c, colmap=cm, lse_out=lse[s * n_r:(s + 1) * n_r])
-            S.append(Ss)
+        # every term in one launch per stage: term s reads columns through the map (blk = 2b, ld = nseg * 2b, base = s * 2b)
+        losses, lse, Sall = ops.ntxent_pack_fwd(z, nseg, zc, b, col_offset, half, temperature, n_c, (n_r, n, 0), n_r)
+        S = [Sall[s] for s in range(nseg)]
         if dist is not None:
             lse_all = torch.empty(W * n, dtype=F32, device=dev)
             dist.all_gather_into_tensor(lse_all, lse)
         else:
             lse_all = lse
-        return losses, dict(z=z, norm=norm, zc=zc, lse_all=lse_all, S=S, b=b, n_r=n_r, n=n, n_c=n_c, col_offset=col_offset,
+        return losses, dict(z=z, norm=norm, zc=zc, lse_all=lse_all, S=S, Sall=Sall, nseg=nseg, b=b, n_r=n_r, n=n, n_c=n_c, col_offset=col_offset,
                             half=half, T=temperature)
 
     @staticmethod
@@ -95,6 +90,19 @@ class _NTXentPack:
         # DDP averages parameter gradients over ranks, so the per-rank seed stays 1/(2b) for any world size
         return ops.ntxent_bwd(sv["z"][sl], sv["norm"][sl], sv["zc"], sv["lse_all"], S, b, sv["col_offset"], sv["half"],
                               sv["T"], gscale / (2 * b), upstream, n_c=sv["n_c"], colmap=(n_r, sv["n"], seg * n_r))
+
+
+    @staticmethod
+    def bwd_all(sv, gscales, upstream=None):
+        """-> gradient [nseg * 2b, D] w.r.t. the packed rows, every term in one launch per stage."""
+        if any(S is None for S in sv["S"]):
+            raise RuntimeError("NT-Xent backward ran twice on one forward: its logits scratch is overwritten in place by "
+                               "the first backward (retain_graph=True is not supported by this fused loss)")
+        nseg, n_r, b = sv["nseg"], sv["n_r"], sv["b"]
+        sv["S"] = [None] * nseg
+        return ops.ntxent_pack_bwd(sv["z"], sv["norm"], nseg, sv["zc"], sv["lse_all"], sv["Sall"], b, sv["col_offset"],
+                                   sv["half"], sv["T"], [g / (2 * b) for g in gscales], upstream, sv["n_c"],
+                                   (n_r, sv["n"], 0), n_r)
 
 
 class _NTXentFn(torch.autograd.Function):
@@ -193,8 +201,8 @@ class _PretrainLossFn(torch.autograd.Function):
     def backward(ctx, dtotal):
         saved, b, w = ctx.saved
         up = dtotal.float().contiguous()[0:1]      # gradients flow through total[0] only (entries 1,2 are for logging)
-        d_imid = _NTXentPack.bwd(saved, 0, 1.0, up)               # [2b, D] w.r.t. [t1; t2]
-        d_cmid = _NTXentPack.bwd(saved, 1, w, up)                 # [2b, D] w.r.t. [(t1+t2)/2; img]
+        d_all = _NTXentPack.bwd_all(saved, (1.0, w), up)          # one launch per stage for both terms
+        d_imid, d_cmid = d_all[:2 * b], d_all[2 * b:]             # w.r.t. [t1; t2] and [(t1+t2)/2; img]
         half = ops.add_scale(d_cmid[:b], None, 0.5)
         dpc = torch.empty_like(d_imid)
         ops.add_scale(d_imid[:b], half, 1.0, out=dpc[:b])

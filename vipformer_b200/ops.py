@@ -155,7 +155,7 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, drop_p=0.0, seed=None, op_id=0):
 
 def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Lq, Lk, scale, drop_p=0.0, seed=None, op_id=0):
     assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0)
-    delta = torch.empty((B * H, Lq), dtype=F32, device=q.device)
+    delta = torch.empty(_ws("vpf_attention_bwd_workspace_bytes", B, H, Lq) // 4, dtype=F32, device=q.device)
     _lib.call("vpf_attention_bwd", _p(q), _i(q.stride(0)), _p(k), _p(v), _i(k.stride(0)), _p(o), _i(o.stride(0)),
               _p(do), _i(do.stride(0)), _p(lse), _p(delta), _p(dq), _i(dq.stride(0)), _p(dk), _p(dv),
               _i(dk.stride(0)), _i(B), _i(H), _i(Lq), _i(Lk), _i(64), _f(scale), _f(drop_p), _p(seed), _u(op_id), _s())
@@ -230,7 +230,7 @@ def bn_backward(dy, x, st, relu, dgamma, dbeta, out_dtype=BF16):
         raise NotImplementedError("backward through an eval-mode BatchNorm1d (running statistics) is not built; "
                                   "call .train() on the module before a forward you backpropagate through")
     R, C = x.shape
-    red = torch.empty(3 * C, dtype=torch.float64, device=x.device)
+    red = torch.empty(_ws("vpf_bn_bwd_workspace_bytes", C) // 8, dtype=torch.float64, device=x.device)
     dx = torch.empty((R, C), dtype=out_dtype, device=x.device)
     _lib.call("vpf_bn_bwd", _p(dy), _isbf(dy), _p(x), _isbf(x), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd),
               _i(int(relu)), _p(red), _p(dx), _isbf(dx), _p(dgamma), _p(dbeta), _ll(R), _i(C), _s())
@@ -296,7 +296,7 @@ def linear3_bwd(dy, p, ldp, dW, db, R):
 
 def linear3_bn_bwd(dh, p, ldp, w, b, st, dW, db, dgamma, dbeta, R):
     Co = w.shape[0]
-    red = torch.empty(2 * Co, dtype=torch.float64, device=p.device)
+    red = torch.empty(_ws("vpf_linear3_bn_bwd_workspace_bytes", Co) // 8, dtype=torch.float64, device=p.device)
     _lib.call("vpf_linear3_bn_bwd", _p(dh), _p(p), _i(ldp), _p(w), _p(b), _p(st.scale), _p(st.shift), _p(st.mean),
               _p(st.rstd), _p(red), _p(dW), _p(db), _p(dgamma), _p(dbeta), _ll(R), _i(Co), _s())
 
@@ -327,7 +327,7 @@ def ntxent_fwd(zr, zc, b_local, col_offset, half, temperature, loss_out, n_c=Non
     n_c = zc.shape[0] if n_c is None else n_c
     blk, ld, base = (n_c, n_c, 0) if colmap is None else colmap
     lse = torch.empty(n_r, dtype=F32, device=zr.device) if lse_out is None else lse_out
-    S = torch.empty((n_r, n_c), dtype=F32, device=zr.device)
+    S = torch.empty(_ws("vpf_ntxent_logits_workspace_bytes", n_r, n_c) // 4, dtype=F32, device=zr.device).view(n_r, n_c)
     _lib.call("vpf_ntxent_fwd", _p(zr), _i(n_r), _p(zc), _i(n_c), _i(D), _i(b_local), _i(col_offset), _i(half),
               _i(blk), _i(ld), _i(base), _f(temperature), _p(S), _p(lse), _p(loss_out), _s())
     return lse, S
@@ -339,16 +339,54 @@ def ntxent_bwd(zr, norm, zc, lse_all, S, b_local, col_offset, half, temperature,
     n_c = zc.shape[0] if n_c is None else n_c
     blk, ld, base = (n_c, n_c, 0) if colmap is None else colmap
     dx = torch.empty((n_r, D), dtype=F32, device=zr.device)
-    G = torch.empty((n_r, D), dtype=F32, device=zr.device)
+    G = torch.empty(_ws("vpf_ntxent_grad_workspace_bytes", n_r, D) // 4, dtype=F32, device=zr.device)
     _lib.call("vpf_ntxent_bwd", _p(zr), _p(norm), _i(n_r), _p(zc), _p(lse_all), _i(n_c), _i(D), _i(b_local),
               _i(col_offset), _i(half), _i(blk), _i(ld), _i(base), _f(temperature), _f(gscale), _p(upstream), _p(S), _p(G),
               _p(dx), _s())
     return dx
 
 
+def ntxent_pack_fwd(z, nseg, zc, b_local, col_offset, half, temperature, n_c, colmap, base_stride):
+    """nseg loss terms in one launch per stage: z [nseg * n_r, D] -> (losses [nseg], lse [nseg * n_r], S [nseg, n_r, n_c])."""
+    n, D = z.shape
+    n_r = n // nseg
+    blk, ld, base = colmap
+    losses = zeros_(torch.empty(nseg, dtype=F32, device=z.device))
+    lse = torch.empty(n, dtype=F32, device=z.device)
+    S = torch.empty(nseg * _ws("vpf_ntxent_logits_workspace_bytes", n_r, n_c) // 4, dtype=F32, device=z.device).view(nseg, n_r, n_c)
+    _lib.call("vpf_ntxent_pack_fwd", _p(z), _i(nseg), _i(n_r), _p(zc), _i(n_c), _i(D), _i(b_local), _i(col_offset), _i(half),
+              _i(blk), _i(ld), _i(base), _i(base_stride), _f(temperature), _p(S), _p(lse), _p(losses), _s())
+    return losses, lse, S
+
+
+def ntxent_pack_bwd(z, norm, nseg, zc, lse_all, S, b_local, col_offset, half, temperature, gscales, upstream, n_c, colmap,
+                    base_stride):
+    """-> dx [nseg * n_r, D]; gscales: one host float per term."""
+    n, D = z.shape
+    n_r = n // nseg
+    blk, ld, base = colmap
+    dx = torch.empty((n, D), dtype=F32, device=z.device)
+    G = torch.empty(nseg * _ws("vpf_ntxent_grad_workspace_bytes", n_r, D) // 4, dtype=F32, device=z.device)
+    gs = (ctypes.c_float * nseg)(*[float(g) for g in gscales])
+    _lib.call("vpf_ntxent_pack_bwd", _p(z), _p(norm), _i(nseg), _i(n_r), _p(zc), _p(lse_all), _i(n_c), _i(D), _i(b_local),
+              _i(col_offset), _i(half), _i(blk), _i(ld), _i(base), _i(base_stride), _f(temperature), gs, _p(upstream), _p(S),
+              _p(G), _p(dx), _s())
+    return dx
+
+
 def adamw(p, g, m, v, shadow, lr_ptr, step_ptr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
     _lib.call("vpf_adamw", _p(p), _p(g), _p(m), _p(v), _p(shadow), _ll(p.numel()), _p(lr_ptr), _f(beta1), _f(beta2),
               _f(eps), _f(weight_decay), _p(step_ptr), _f(grad_scale), _s())
+
+
+def draw_indices(state, op_id, N, out):
+    """out int64 [n] <- uniform indices in [0, N) from the device step state (engine: FPS start points, utils.py:71)."""
+    _lib.call("vpf_draw_indices", _p(state), _u(op_id), _i(out.numel()), _i(N), _p(out), _s())
+    return out
+
+
+def _ws(name, *dims):
+    return int(_lib.size_query(name, *[_i(d) for d in dims]))
 
 
 def step_advance(state):
