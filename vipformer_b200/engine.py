@@ -12,6 +12,8 @@ B200-first structure:
     log-sum-exp, SURVEY.md 8e); BatchNorm statistics stay rank-local exactly like the reference (no SyncBN);
   * GradScaler (pretrain.py:154,209-211) is dropped: bf16 operands with fp32 accumulation need no loss scaling.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -67,6 +69,8 @@ class PretrainEngine:
         self.arena.refresh_shadows(force=True)
         self.arena.managed = True
         n = self.arena.flat_p.numel()
+        n_pc_params = len(list(self.pc_model.parameters()))
+        self.n_pc = self.arena._offsets[n_pc_params] if n_pc_params < len(self.arena._offsets) else n   # first image-model element
         self.m = ops.zeros_(torch.empty(n, dtype=F32, device=self.device))
         self.v = ops.zeros_(torch.empty(n, dtype=F32, device=self.device))
         self.lr = torch.tensor([lr], dtype=F32, device=self.device)
@@ -88,6 +92,10 @@ class PretrainEngine:
         self.use_graph = use_cuda_graph
         self.graph = None
         self.side = torch.cuda.Stream(device=self.device) if overlap_branches else None
+        self.overlap_allreduce = os.environ.get("VPF_AR_OVERLAP", "1") != "0"
+        self._img_after_g2e = self.side is not None and os.environ.get("VPF_IMG_AFTER_G2E", "1") != "0"
+        if self._img_after_g2e:
+            self.pc_model.group2emb.register_forward_hook(lambda m, i, o: self._g2e_done.record())
         self._copy_stream, self._staged = None, False
         self._loss_ring, self._loss_pending = None, None
         self.steps_done = 0
@@ -107,20 +115,48 @@ class PretrainEngine:
             # kernels fill the partial last waves / launch gaps of the point-cloud branch (autograd replays each
             # node's backward on the stream its forward ran on, so the backward overlaps the same way)
             cur = torch.cuda.current_stream()
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                img_feats, _ = self.img_model(imgs)       # pretrain.py:199
-            pc_feats, _ = self.pc_model(self.pc_in)       # pretrain.py:186
+            if not self._img_after_g2e:
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    img_feats, _ = self.img_model(imgs)       # pretrain.py:199
+                pc_feats, _ = self.pc_model(self.pc_in)       # pretrain.py:186
+            else:
+                # The image forward starts when the point-cloud branch leaves Group2Emb (event recorded by a forward hook):
+                # the tokenizer + Group2Emb kernels are few and large and gain nothing from a neighbour, the ~170
+                # 20-70 us kernels of the point-cloud encoder behind them do (their launch gaps and partial last waves get
+                # filled).  Measured -0.1 ... -0.3 ms per step against starting both branches together.
+                self._g2e_done = torch.cuda.Event()
+                pc_feats, _ = self.pc_model(self.pc_in)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(self._g2e_done)
+                    img_feats, _ = self.img_model(imgs)
             cur.wait_stream(self.side)
         else:
             pc_feats, _ = self.pc_model(self.pc_in)
             img_feats, _ = self.img_model(imgs)
         losses = pretrain_loss(pc_feats, img_feats, self.temperature, self.cmid_weight, self.gather)
-        losses[0].backward()                              # pretrain.py:209
-        if self.side is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
-        if self.dist:                                     # DDP gradient all-reduce (mean), one flat buffer
-            self.dist.all_reduce(self.arena.flat_g, op=self.dist.ReduceOp.AVG)
+        if self.dist and self.side is not None and self.overlap_allreduce:
+            # DDP-style overlap without per-parameter hooks: backward in three pieces.  (1) the loss node alone; (2) the image
+            # branch, launched from its own stream, followed at once by the all-reduce of ITS slice of the flat gradient
+            # buffer (parameters are laid out [point-cloud model | image model]); (3) the point-cloud branch, whose longer
+            # backward (Group2Emb, 2048-key cross-attention) hides that transfer.  Only the point-cloud slice is reduced
+            # after the backward.  All collectives stay on the launching thread, so the step still captures as one graph.
+            cur = torch.cuda.current_stream()
+            d_pc, d_img = torch.autograd.grad(losses[0], [pc_feats, img_feats])
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                torch.autograd.backward([img_feats], [d_img])
+                work = self.dist.all_reduce(self.arena.flat_g[self.n_pc:], op=self.dist.ReduceOp.AVG, async_op=True)
+            torch.autograd.backward([pc_feats], [d_pc])
+            cur.wait_stream(self.side)
+            self.dist.all_reduce(self.arena.flat_g[:self.n_pc], op=self.dist.ReduceOp.AVG)
+            work.wait()
+        else:
+            losses[0].backward()                              # pretrain.py:209
+            if self.side is not None:
+                torch.cuda.current_stream().wait_stream(self.side)
+            if self.dist:                                     # DDP gradient all-reduce (mean), one flat buffer
+                self.dist.all_reduce(self.arena.flat_g, op=self.dist.ReduceOp.AVG)
         ops.adamw(self.arena.flat_p, self.arena.flat_g, self.m, self.v, self.arena.flat_bf, self.lr, self.state[:1],
                   self.betas[0], self.betas[1], self.eps, self.weight_decay)   # pretrain.py:210
         ops.add_scale(losses.detach(), None, 1.0, out=self.losses)

@@ -13,6 +13,7 @@ import torch.nn as nn
 from . import _lib, ops
 
 F32 = torch.float32
+_SERIAL_TERMS = __import__("os").environ.get("VPF_NTXENT_SERIAL", "0") == "1"
 
 
 def _dist():
@@ -69,6 +70,10 @@ class _NTXentPack:
         # every term in one launch per stage: term s reads columns through the map (blk = 2b, ld = nseg * 2b, base = s * 2b)
         losses, lse, Sall = ops.ntxent_pack_fwd(z, nseg, zc, b, col_offset, half, temperature, n_c, (n_r, n, 0), n_r)
         S = [Sall[s] for s in range(nseg)]
+        if _SERIAL_TERMS:       # measurement switch (tools/ablate_step.py): one launch chain per term, as before the packing
+            for s in range(1, nseg):
+                ops.ntxent_fwd(z[s * n_r:(s + 1) * n_r], zc, b, col_offset, half, temperature, losses[s:s + 1],
+                               n_c=n_c, colmap=(n_r, n, s * n_r), lse_out=lse[s * n_r:(s + 1) * n_r])
         if dist is not None:
             lse_all = torch.empty(W * n, dtype=F32, device=dev)
             dist.all_gather_into_tensor(lse_all, lse)
@@ -201,8 +206,11 @@ class _PretrainLossFn(torch.autograd.Function):
     def backward(ctx, dtotal):
         saved, b, w = ctx.saved
         up = dtotal.float().contiguous()[0:1]      # gradients flow through total[0] only (entries 1,2 are for logging)
-        d_all = _NTXentPack.bwd_all(saved, (1.0, w), up)          # one launch per stage for both terms
-        d_imid, d_cmid = d_all[:2 * b], d_all[2 * b:]             # w.r.t. [t1; t2] and [(t1+t2)/2; img]
+        if _SERIAL_TERMS:
+            d_imid, d_cmid = _NTXentPack.bwd(saved, 0, 1.0, up), _NTXentPack.bwd(saved, 1, w, up)
+        else:
+            d_all = _NTXentPack.bwd_all(saved, (1.0, w), up)          # one launch per stage for both terms
+            d_imid, d_cmid = d_all[:2 * b], d_all[2 * b:]             # w.r.t. [t1; t2] and [(t1+t2)/2; img]
         half = ops.add_scale(d_cmid[:b], None, 0.5)
         dpc = torch.empty_like(d_imid)
         ops.add_scale(d_imid[:b], half, 1.0, out=dpc[:b])
