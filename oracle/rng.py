@@ -28,21 +28,26 @@ def make_key(seed, op_id):
     return int(mix32(lo ^ inner))
 
 
-def threshold(p):
-    t = float(np.float32(p)) * 4294967296.0
-    return 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+def threshold8(p):
+    """rng.cuh threshold8: drop iff byte < round(256 p) (clamped to 255)."""
+    if not p > 0.0:
+        return 0
+    return min(255, int(float(np.float32(p)) * 256.0 + 0.5))
 
 
 def residual_keep(seed, op_id, p, rows, cols):
-    """Residual dropout mask of a [rows, cols] GEMM output (gemm.cu epilogue, dropout_grad): element index
-    row * cols + col; returns float32 mask already scaled by 1 / (1 - p)."""
-    if p <= 0.0:
+    """Residual / Dropout mask of a [rows, cols] tensor (gemm.cu residual epilogue, dropout_grad; rng.cuh keep8): element
+    index e = row * cols + col keeps iff byte (e & 3) of hash(key, e >> 2) >= round(256 p); returns the float32 mask
+    already scaled by 256 / (256 - round(256 p))  (p = 0.5 exact, p = 0.1 -> 26/256)."""
+    thr = threshold8(p)
+    if thr == 0:
         return np.ones((rows, cols), np.float32)
     key = np.uint64(make_key(seed, op_id))
     idx = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(cols) + np.arange(cols, dtype=np.uint64)[None, :]) & _M
-    h = mix32(((idx * np.uint64(0x9E3779B1)) & _M) ^ key)
-    keep = h >= np.uint64(threshold(p))
-    return keep.astype(np.float32) * np.float32(1.0 / (1.0 - float(np.float32(p))))
+    h = mix32((((idx >> np.uint64(2)) * np.uint64(0x9E3779B1)) & _M) ^ key)
+    byte = (h >> ((idx & np.uint64(3)) * np.uint64(8))) & np.uint64(0xFF)
+    keep = byte >= np.uint64(thr)
+    return keep.astype(np.float32) * np.float32(256.0 / (256.0 - thr))
 
 
 def attention_keep(seed, op_id, p, BH, Lq, Lk):

@@ -236,6 +236,27 @@ def test_dropout_grad_and_colsum():
     close(s[96:], (x.double() ** 2).sum(0), tol=1e-5)
 
 
+@pytest.mark.parametrize("T,N,p", [(2048, 256, 0.5), (300, 96, 0.1), (77, 384, 0.5), (130, 72, 0.1)])
+def test_residual_dropout_mask_equals_the_oracle_restatement(T, N, p):
+    """Byte-granular Residual masks (rng.cuh keep8): dropout_grad and the GEMM residual epilogue draw exactly the mask
+    oracle/rng.py restates, scale 256 / (256 - round(256 p)) included."""
+    import oracle.rng as R
+    from vipformer_b200 import ops
+
+    g = rnd((T, N), 3) + 3.0          # no zeros in the data: out == 0 <=> dropped
+    seed = torch.tensor([0x1234567 + T], device="cuda", dtype=torch.int64)
+    m = torch.from_numpy(R.residual_keep(int(seed.item()), 11, p, T, N)).cuda()
+    out = ops.dropout_grad(g, p, seed, 11)
+    assert torch.equal(out != 0, m != 0)
+    close(out, g * m, bf16=True)
+    A = torch.eye(N, device="cuda", dtype=BF16)
+    o = torch.empty((T, N), device="cuda")
+    ops.gemm(g.to(BF16), A, o, mode=ops.EPI_RESIDUAL, resid=torch.zeros_like(g), drop_p=p, seed=seed, op_id=11)
+    assert torch.equal(o != 0, m != 0)
+    close(o, g.to(BF16).float() * m, tol=1e-5)
+    assert abs((m != 0).float().mean().item() - (1 - R.threshold8(p) / 256)) < 0.02
+
+
 def test_group_max_and_token_pool():
     from vipformer_b200 import ops
 

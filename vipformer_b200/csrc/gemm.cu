@@ -188,9 +188,9 @@ __device__ __forceinline__ void epilogue_wa(const GemmArgs &g, const CUtensorMap
   uint32_t drop_thr = 0, drop_key = 0;
   float drop_scale = 1.f;
   if (resid && e.drop_p > 0.f) {
-    drop_thr = rng::threshold(e.drop_p);
+    drop_thr = rng::threshold8(e.drop_p);
     drop_key = rng::make_key(e.seed_ptr ? *e.seed_ptr : 0ull, e.op_id);
-    drop_scale = 1.f / (1.f - e.drop_p);
+    drop_scale = rng::scale8(drop_thr);
   }
   const bool bias_vec = (e.bias || has_rg) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) &&
                         (!has_rg || ((reinterpret_cast<uintptr_t>(e.rg_bias) & 15) == 0 && (e.rg_ld & 3) == 0));
@@ -319,8 +319,7 @@ __device__ __forceinline__ void epilogue_wa(const GemmArgs &g, const CUtensorMap
         if (resid) {   // out = resid + dropout(v)   (Residual, partseg.py:208-213), in place in the staging chunk
           if (drop_thr) {
             const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col0);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = rng::keep(drop_key, ebase + j, drop_thr) ? v[j] * drop_scale : 0.f;
+            rng::drop_values<32>(v, drop_key, ebase, drop_thr, drop_scale, (g.N & 3) == 0);
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -547,9 +546,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t drop_thr = 0, drop_key = 0;
     float drop_scale = 1.f;
     if (e.mode == VPF_EPI_RESIDUAL && e.drop_p > 0.f) {
-      drop_thr = rng::threshold(e.drop_p);
+      drop_thr = rng::threshold8(e.drop_p);
       drop_key = rng::make_key(e.seed_ptr ? *e.seed_ptr : 0ull, e.op_id);
-      drop_scale = 1.f / (1.f - e.drop_p);
+      drop_scale = rng::scale8(drop_thr);
     }
     // vector (16-byte) bias loads need aligned pointers; otherwise the scalar path after the wait is used
     const bool bias_vec = (e.bias || e.rg_bias) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) &&
@@ -674,7 +673,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 if (e.out_f32) reinterpret_cast<float *>(e.out)[off] = x;
                 else reinterpret_cast<__nv_bfloat16 *>(e.out)[off] = __float2bfloat16(x);
               } else if (e.mode == VPF_EPI_RESIDUAL) {
-                if (drop_thr) x = rng::keep(drop_key, (uint32_t)((size_t)grow * g.N + col0 + j), drop_thr) ? x * drop_scale : 0.f;
+                if (drop_thr) x = rng::keep8(drop_key, (uint32_t)((size_t)grow * g.N + col0 + j), drop_thr) ? x * drop_scale : 0.f;
                 reinterpret_cast<float *>(e.out)[off] = x + e.resid[off];
               } else {
                 atomicAdd(reinterpret_cast<float *>(e.out) + off, x);
@@ -770,8 +769,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (e.mode == VPF_EPI_RESIDUAL) {   // out = resid + dropout(v)   (Residual, partseg.py:208-213); in place in smem
           if (drop_thr) {
             const uint32_t ebase = (uint32_t)((size_t)grow * g.N + col0);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = rng::keep(drop_key, ebase + j, drop_thr) ? v[j] * drop_scale : 0.f;
+            rng::drop_values<32>(v, drop_key, ebase, drop_thr, drop_scale, (g.N & 3) == 0);
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {

@@ -264,16 +264,16 @@ __global__ void __launch_bounds__(256)
 dropout_grad_kernel(const float *__restrict__ g, __nv_bfloat16 *__restrict__ out, float *__restrict__ colsum,
                     float p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id, int T, int N,
                     int rows_per_cta) {
-  const uint32_t thr = p > 0.f ? rng::threshold(p) : 0u;
-  const uint32_t key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
-  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const uint32_t thr = rng::threshold8(p);
+  const uint32_t key = thr ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
+  const float scale = rng::scale8(thr);
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
   for (int c = threadIdx.x; c < N; c += 256) {
     float acc = 0.f;
     for (int r = row0; r < row1; ++r) {
       const size_t e = (size_t)r * N + c;
       float v = g[e];
-      if (thr) v = rng::keep(key, (uint32_t)e, thr) ? v * scale : 0.f;
+      if (thr) v = rng::keep8(key, (uint32_t)e, thr) ? v * scale : 0.f;
       out[e] = __float2bfloat16(v);
       acc += v;
     }
@@ -289,9 +289,9 @@ dropout_grad_vec_kernel(const float *__restrict__ g, __nv_bfloat16 *__restrict__
                         float p, const unsigned long long *__restrict__ seed_ptr, uint32_t op_id, int T, int N,
                         int rows_per_cta) {
   __shared__ float s_sum[1024];
-  const uint32_t thr = p > 0.f ? rng::threshold(p) : 0u;
-  const uint32_t key = p > 0.f ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
-  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const uint32_t thr = rng::threshold8(p);
+  const uint32_t key = thr ? rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id) : 0u;
+  const float scale = rng::scale8(thr);
   const int lanes = N >> 2, ny = 256 / lanes;
   const int tx = threadIdx.x % lanes, ty = threadIdx.x / lanes;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
@@ -310,9 +310,8 @@ dropout_grad_vec_kernel(const float *__restrict__ g, __nv_bfloat16 *__restrict__
         if (rr >= row1) continue;
         float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         if (thr) {
-          const uint32_t e = (uint32_t)((size_t)rr * N) + 4u * tx;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) f[q] = rng::keep(key, e + q, thr) ? f[q] * scale : 0.f;
+          const uint32_t e = (uint32_t)((size_t)rr * N) + 4u * tx;      // N % 4 == 0 on this path: one hash per thread and row
+          rng::drop_values<4>(f, key, e, thr, scale, true);
         }
         const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
         uint2 pk;

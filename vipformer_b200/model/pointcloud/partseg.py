@@ -34,6 +34,9 @@ from ...runtime import (StepState as _StepState, advance_dropout_seed, anchor as
                         set_root as _set_root)
 
 
+_TOK_STREAM = __import__("os").environ.get("VPF_TOK_STREAM", "1") != "0"
+
+
 # ------------------------------------------------------------------------------------- parameter containers
 class MultiHeadAttention(nn.Module):
     def __init__(self, num_heads: int, num_q_input_channels: int, num_kv_input_channels: int,
@@ -518,9 +521,21 @@ class CrossFormer_pc_mp(nn.Module):
         if self.__dict__.get("_vpf_root") is None:
             _set_root(self)
         pts = pts.float().contiguous()
-        pts_embs = self.input_adapter(pts)
-        neighborhood, center = divide_patches(pts, self.num_groups, self.group_size, start_idx=self.fps_start_idx,
-                                              generator=self.fps_generator)
+        if _TOK_STREAM and pts.is_cuda:
+            # FPS / kNN are instruction-issue bound and touch ~1 % of the HBM bandwidth, the input adapter (point-wise MLP over
+            # every point) is the opposite: run them side by side, the tokenizer on an auxiliary stream
+            cur, aux = torch.cuda.current_stream(), _rt.aux_stream(pts.device)
+            start = self.fps_start_idx
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                neighborhood, center = divide_patches(pts, self.num_groups, self.group_size, start_idx=start,
+                                                      generator=self.fps_generator)
+            pts_embs = self.input_adapter(pts)
+            cur.wait_stream(aux)
+        else:
+            pts_embs = self.input_adapter(pts)
+            neighborhood, center = divide_patches(pts, self.num_groups, self.group_size, start_idx=self.fps_start_idx,
+                                                  generator=self.fps_generator)
         group_embs = self.group2emb(neighborhood)
         pos_embs = self.position_emb(center)
         return self.encoder(group_embs, pos_embs, pts_embs)

@@ -52,6 +52,19 @@ def next_op_offset(managed):
     return _EPOCH[0] * EPOCH_STRIDE
 
 
+# ---- auxiliary stream of a device (tokenizer next to the input adapter, CrossFormer_pc_mp._tokens)
+_AUX = {}
+
+
+def aux_stream(device):
+    import torch
+
+    key = torch.device(device).index
+    if key not in _AUX:
+        _AUX[key] = torch.cuda.Stream(device=device)
+    return _AUX[key]
+
+
 # ---- test tap: when set to a dict, block forwards drop their saved context here (discrete choices for parity tests)
 TAP = None
 
