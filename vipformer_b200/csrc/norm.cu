@@ -42,10 +42,72 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p,
 }
 
 // ------------------------------------------------------------- LayerNorm fwd
-// One warp per row, NPER = D/32 values per lane held in registers.  VEC: lane owns float4 groups (D % 128 == 0).
-// The grid is the resident set (SMs x occupancy) and every warp strides over the rows with the NEXT row's loads issued
-// before the current row is reduced and stored: two rows of loads in flight per warp, no CTA turnover
-// (the 8-rows-per-CTA version ran at 60 % of the HBM copy rate).
+// one warp per row; NPER = D/32 values per lane held in registers.  VEC: lane owns float4 groups (D % 128 == 0).
+template <typename Tin, int NPER, bool VEC>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
+              const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
+              float *__restrict__ mean_out, float *__restrict__ rstd_out, int T, float eps, int relu) {
+  constexpr int D = NPER * 32;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  float v[NPER];
+  float s = 0.f;
+  if constexpr (VEC) {
+#pragma unroll
+    for (int q = 0; q < NPER / 4; ++q) {
+      const int c = (lane + 32 * q) * 4;
+      float4 t = ld4<Tin>(x, (size_t)row * D + c);
+      if (add) {
+        const float4 a = ld4<float>(add, (size_t)(row % add_rows) * D + c);
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+      }
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      s += (t.x + t.y) + (t.z + t.w);
+      if (xsum) st4<float>(xsum, (size_t)row * D + c, t);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float t = ldf<Tin>(x, (size_t)row * D + c);
+      if (add) t += add[(size_t)(row % add_rows) * D + c];
+      v[i] = t;
+      s += t;
+      if (xsum) xsum[(size_t)row * D + c] = t;
+    }
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) { const float d = v[i] - mean; q2 += d * d; }
+  const float rstd = rsqrtf(warp_sum(q2) * (1.f / D) + eps);
+  if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
+  if constexpr (VEC) {
+#pragma unroll
+    for (int q = 0; q < NPER / 4; ++q) {
+      const int c = (lane + 32 * q) * 4;
+      const float4 g = ld4<float>(gamma, c), b = ld4<float>(beta, c);
+      float4 o = make_float4((v[4 * q] - mean) * rstd * g.x + b.x, (v[4 * q + 1] - mean) * rstd * g.y + b.y,
+                             (v[4 * q + 2] - mean) * rstd * g.z + b.z, (v[4 * q + 3] - mean) * rstd * g.w + b.w);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4<__nv_bfloat16>(y, (size_t)row * D + c, o);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int c = lane + 32 * i;
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (relu) o = fmaxf(o, 0.f);
+      y[(size_t)row * D + c] = __float2bfloat16(o);
+    }
+  }
+}
+
+// Row-striding variant for narrow rows (D <= 128): the grid is the resident set and every warp walks the rows with the NEXT
+// row's loads issued before the current row is reduced -- at D = 64 (the input adapter's LayerNorm over every point) the
+// one-row-per-warp kernel above spends its time on CTA turnover: 156 -> 125 us per 1 M rows.  At D = 256 the prefetch
+// registers halve the occupancy and it measured slower (256 vs 213 us), so wide rows keep the kernel above.
 template <typename Tin, int NPER, bool VEC>
 __device__ __forceinline__ void ln_load_row(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, int row,
                                             int lane, float (&v)[NPER]) {
@@ -74,7 +136,7 @@ __device__ __forceinline__ void ln_load_row(const Tin *__restrict__ x, const flo
 
 template <typename Tin, int NPER, bool VEC>
 __global__ void __launch_bounds__(256)
-ln_fwd_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
+ln_fwd_rows_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int add_rows, float *__restrict__ xsum,
               const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y,
               float *__restrict__ mean_out, float *__restrict__ rstd_out, int T, float eps, int relu) {
   constexpr int D = NPER * 32;
@@ -765,18 +827,20 @@ int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows,
   VPF_REQUIRE(!add || add_rows > 0, "layernorm_fwd: add_rows must be > 0");
   if (T == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#define LNF_CALL(TIN, NP, VEC)                                                                                      \
+  const int grid = ceil_div(T, 8);   // 8 rows per CTA: a row-striding resident grid with the next row prefetched measured slower
+                                     // (64 registers -> half the warps per SM: 256 vs 213 us on the 1 M-row kv_norm)
+#define LNF_ROWS(TIN, NP, VEC)                                                                                      \
   {                                                                                                                 \
-    VPF_RESIDENT_CTAS(slots, (ln_fwd_kernel<TIN, NP, VEC>), 256, 0);                                                 \
-    const int grid = min(ceil_div(T, 8), slots);                                                                    \
-    ln_fwd_kernel<TIN, NP, VEC><<<grid, 256, 0, st>>>((const TIN *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
+    VPF_RESIDENT_CTAS(slots, (ln_fwd_rows_kernel<TIN, NP, VEC>), 256, 0);                                            \
+    ln_fwd_rows_kernel<TIN, NP, VEC><<<min(grid, slots), 256, 0, st>>>((const TIN *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
   }
-#define LNF(NP, VEC)                          \
-  if (x_bf16) LNF_CALL(bf16, NP, VEC)         \
-  else LNF_CALL(float, NP, VEC)
+#define LNF(NP, VEC)                                                                                                \
+  if (NP <= 4) { if (x_bf16) LNF_ROWS(bf16, NP, VEC) else LNF_ROWS(float, NP, VEC) }                                \
+  else if (x_bf16) ln_fwd_kernel<bf16, NP, VEC><<<grid, 256, 0, st>>>((const bf16 *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu); \
+  else ln_fwd_kernel<float, NP, VEC><<<grid, 256, 0, st>>>((const float *)x, add, add_rows, xsum, gamma, beta, (bf16 *)y_bf16, mean, rstd, T, eps, relu)
   LN_DISPATCH(D, LNF)
 #undef LNF
-#undef LNF_CALL
+#undef LNF_ROWS
   return check_launch("ln_fwd_kernel");
 }
 
