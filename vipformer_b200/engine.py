@@ -95,7 +95,8 @@ class PretrainEngine:
         self.overlap_allreduce = os.environ.get("VPF_AR_OVERLAP", "1") != "0"
         self._img_after_g2e = self.side is not None and os.environ.get("VPF_IMG_AFTER_G2E", "1") != "0"
         if self._img_after_g2e:
-            self.pc_model.group2emb.register_forward_hook(lambda m, i, o: self._g2e_done.record())
+            self._g2e_done = None      # armed only inside _step_body: the hook is inert when the model is called on its own
+            self.pc_model.group2emb.register_forward_hook(lambda m, i, o: self._g2e_done.record() if self._g2e_done is not None else None)
         self._copy_stream, self._staged = None, False
         self._loss_ring, self._loss_pending = None, None
         self.steps_done = 0
@@ -130,6 +131,7 @@ class PretrainEngine:
                 with torch.cuda.stream(self.side):
                     self.side.wait_event(self._g2e_done)
                     img_feats, _ = self.img_model(imgs)
+                self._g2e_done = None
             cur.wait_stream(self.side)
         else:
             pc_feats, _ = self.pc_model(self.pc_in)
