@@ -192,3 +192,25 @@ def test_interp3_forward_backward_match_torch():
         for j in range(3):
             dref[b].index_add_(0, idx[b, :, j].long(), dout.float().view(B, N, -1)[b, :, :C] * w[b, :, j:j + 1])
     assert relfro(dfe, dref) < 1e-5
+
+
+def test_partseg_guards_and_four_taps():
+    """layer_idx of any length >= 1 (the reference hard-codes 3 or 4, partseg.py:424-428); N must be a power of two here."""
+    cfg = dict(_synth.SEG_CASES["seg_small"], layer_idx=[1, 2, 3, 4])
+    model = _synth.build_seg_model(cfg).cuda().train()
+    pts, start, onehot, labels = _synth.seg_inputs(cfg)
+    model.fps_start_idx = torch.from_numpy(start).cuda()
+    out = model(pts.cuda(), onehot.cuda())
+    assert out.shape == (cfg["b"], cfg["N"], cfg["parts"]) and torch.isfinite(out).all()
+    out.float().square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    # taps beyond the last requested layer are not run: layer 4's parameters get no gradient when only 1..2 are tapped
+    m2 = _synth.build_seg_model(dict(cfg, layer_idx=[1, 2])).cuda().train()
+    m2.fps_start_idx = torch.from_numpy(start).cuda()
+    m2(pts.cuda(), onehot.cuda()).float().square().mean().backward()
+    g = m2.encoder.sa_layers[3][1].module[1].weight.grad
+    assert g is None or float(g.abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        model(pts[:, :100].contiguous().cuda(), onehot.cuda())
+    with pytest.raises(ValueError):
+        _synth.build_seg_model(dict(cfg, layer_idx=[9])).cuda()(pts.cuda(), onehot.cuda())

@@ -164,8 +164,8 @@ class PretrainEngine:
         ops.add_scale(losses.detach(), None, 1.0, out=self.losses)
 
     def _snapshot(self):
-        """Everything a step mutates besides the activations: parameters, Adam moments, step/seed state, BatchNorm
-        buffers, the FPS-start generator."""
+        """Everything a step mutates besides the activations: parameters, Adam moments, step/seed state (which also drives
+        the FPS start draw), BatchNorm buffers."""
         return ([t.clone() for t in (self.arena.flat_p, self.arena.flat_bf, self.m, self.v, self.state)],
                 [b.clone() for b in self.root.buffers()])
 
