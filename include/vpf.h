@@ -199,6 +199,11 @@ int vpf_bn_apply(const void *x, int x_bf16, const float *scale, const float *shi
 int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const float *scale,
                const float *shift, const float *mean, const float *rstd, int relu, double *red,
                void *dx, int dx_bf16, float *dgamma, float *dbeta, long long R, int C, void *stream);
+/* The same backward for an all-bf16 [R, 256] tensor fused with the row sum over groups of S consecutive rows of dx
+ * (Group2Emb's split conv3 needs it, utils.py:183-185): gsum_bf16 / gsum_f32 [R/S, 256] (either may be null). */
+int vpf_bn_bwd_gsum(const void *dy_bf16, const void *x_bf16, const float *scale, const float *shift,
+                    const float *mean, const float *rstd, int relu, double *red, void *dx_bf16, float *dgamma,
+                    float *dbeta, long long R, int C, int S, void *gsum_bf16, float *gsum_f32, void *stream);
 /* nn.GELU (exact erf) of the MLP, partseg.py:196, as streaming kernels: h = gelu(z); dz = dh * gelu'(z) with the
  * column sums of dz (bias gradient) accumulated into colsum (optional). */
 int vpf_gelu_fwd(const void *z_bf16, void *h_bf16, long long n, void *stream);

@@ -257,6 +257,31 @@ def test_residual_dropout_mask_equals_the_oracle_restatement(T, N, p):
     assert abs((m != 0).float().mean().item() - (1 - R.threshold8(p) / 256)) < 0.02
 
 
+@pytest.mark.parametrize("G,S", [(300, 32), (17, 8), (5, 33)])
+def test_bn_backward_fused_group_sum(G, S):
+    """vpf_bn_bwd_gsum == vpf_bn_bwd followed by vpf_group_sum (Group2Emb backward), dgamma / dbeta included."""
+    from vipformer_b200 import ops
+
+    R, C = G * S, 256
+    x, dy = rnd((R, C), 1, BF16), rnd((R, C), 2, BF16)
+    w, b = rnd((C,), 3) * 0.2 + 1.0, rnd((C,), 4) * 0.1
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    _, st = ops.bn_forward(x, w, b, rm, rv, True, True)
+    dg0, db0 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx0 = ops.bn_backward(dy, x, st, True, dg0, db0)
+    sb0, sf0 = ops.group_sum(dx0, G, S, C, want_bf16=True, want_f32=True)
+    dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx1, sb1, sf1 = ops.bn_backward_gsum(dy, x, st, True, dg1, db1, S, want_bf16=True, want_f32=True)
+    close(dx1, dx0, bf16=True)
+    close(dg1, dg0, tol=1e-5)
+    close(db1, db0, tol=1e-5)
+    # the fused sum adds the fp32 values before their bf16 rounding; the two-kernel path sums the rounded tensor
+    close(sf1, dx0.float().view(G, S, C).sum(1), tol=2e-2)
+    close(sf1, dx1.float().view(G, S, C).sum(1), tol=2e-2)
+    close(sb1, sf1, bf16=True)
+    close(sf0, sf1, tol=2e-2)
+
+
 def test_group_max_and_token_pool():
     from vipformer_b200 import ops
 

@@ -87,3 +87,15 @@ if not which or "bn" in which:
 
     report("bn_fwd(3 pass)", R, R * C * 2 * 3, fwd)
     report("bn_bwd(2 pass)", R, R * C * 2 * 5, lambda: ops.bn_backward(dyb, xb, st[0], True, dgw, dgb))
+    # Group2Emb's own case: 256 channels, followed by the per-patch row sum (separate kernel vs fused)
+    x2, dy2 = xb[:, :256].contiguous(), dyb[:, :256].contiguous()
+    w2, b2, rm2, rv2 = w[:256].contiguous(), b_[:256].contiguous(), rm[:256].contiguous(), rv[:256].contiguous()
+    dg2, db2 = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+    st2 = ops.bn_forward(x2, w2, b2, rm2, rv2, True, True)[1]
+
+    def two_kernels():
+        d = ops.bn_backward(dy2, x2, st2, True, dg2, db2)
+        ops.group_sum(d, R // 32, 32, 256)
+
+    report("bn_bwd+gsum", R, R * 256 * 2 * 6, two_kernels)
+    report("bn_bwd_gsum", R, R * 256 * 2 * 5, lambda: ops.bn_backward_gsum(dy2, x2, st2, True, dg2, db2, 32))

@@ -635,6 +635,64 @@ bn_bwd_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat
   }
 }
 
+// BN backward apply fused with the per-group row sum that follows it in Group2Emb's backward (the per-patch half of the
+// split conv3 needs sum_{rows of a patch} dx, functional.group2emb_bwd): one WARP owns whole groups of S consecutive rows
+// of a 256-channel tensor -- a row is exactly one 512-byte warp access, lane l owns channels 8l .. 8l+7 -- so the group sums
+// stay in the lane's registers: no shared memory, no barrier, and the 1.07 GB dx tensor is not read again by a second kernel.
+//   dx = a*dyb + b*x + c  with a = scale, b = -scale*rstd*m2, c = scale*(rstd*m2*mean - m1)   (same algebra as above)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_gsum_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ x,
+                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                         const float *__restrict__ rstd, int relu, const float *__restrict__ fm,
+                         __nv_bfloat16 *__restrict__ dx, __nv_bfloat16 *__restrict__ gsum_bf16, float *__restrict__ gsum_f32,
+                         long long G, int S) {
+  constexpr int C = 256;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float sc[8], sh[8], cb[8], cc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane * 8 + q;
+    sc[q] = scale[c]; sh[q] = shift[c];
+    const float t = sc[q] * rstd[c] * fm[C + c];
+    cb[q] = -t;
+    cc[q] = fmaf(t, mean[c], -sc[q] * fm[c]);
+  }
+  for (long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); g < G; g += nwarps) {
+    const size_t base = (size_t)g * S * C + lane * 8;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int r0 = 0; r0 < S; r0 += 4) {
+      uint4 ud[4], ux[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < S) { ud[k] = ldg16(dy + base + (size_t)(r0 + k) * C); ux[k] = ldg16(x + base + (size_t)(r0 + k) * C); }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (r0 + k >= S) continue;
+        float d[8], xv[8];
+        unpack8(ud[k], d);
+        unpack8(ux[k], xv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float dd = d[q];
+          if (relu && !(fmaf(xv[q], sc[q], sh[q]) > 0.f)) dd = 0.f;
+          d[q] = fmaf(sc[q], dd, fmaf(cb[q], xv[q], cc[q]));
+          acc[q] += d[q];
+        }
+        *reinterpret_cast<uint4 *>(dx + base + (size_t)(r0 + k) * C) = pack8(d);
+      }
+    }
+    const size_t o = (size_t)g * C + lane * 8;
+    if (gsum_bf16) *reinterpret_cast<uint4 *>(gsum_bf16 + o) = pack8(acc);
+    if (gsum_f32) {
+      *reinterpret_cast<float4 *>(gsum_f32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4 *>(gsum_f32 + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
 // column sums of a bf16 matrix: fp32 partials per thread, shared-memory combine across ty, one fp64 (or fp32) atomic
 // per column per CTA.  MODE 0: sum (+ sumsq); MODE 1: BN backward phase 1 (sum dyb, sum dyb*xhat)
 template <int MODE>
@@ -998,6 +1056,30 @@ int vpf_bn_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const flo
   else return fail(VPF_EINVAL, "bn_bwd: unsupported dtype combination");
 #undef BNB
   return check_launch("bn_bwd_apply_kernel");
+}
+
+int vpf_bn_bwd_gsum(const void *dy_bf16, const void *x_bf16, const float *scale, const float *shift, const float *mean,
+                    const float *rstd, int relu, double *red, void *dx_bf16, float *dgamma, float *dbeta, long long R, int C,
+                    int S, void *gsum_bf16, float *gsum_f32, void *stream) {
+  VPF_REQUIRE(dy_bf16 && x_bf16 && scale && shift && mean && rstd && red && dx_bf16 && (gsum_bf16 || gsum_f32), "bn_bwd_gsum: null pointer");
+  VPF_REQUIRE(C == 256 && S >= 1 && R % S == 0, "bn_bwd_gsum: needs C == 256 and R %% S == 0 (C=%d S=%d)", C, S);
+  if (R == 0) return VPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VPF_CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st));
+  dim3 g8; int rpc, smem;
+  bf16_col_cfg(R, C, g8, rpc, smem);
+  VPF_RESIDENT_CTAS(slots, colreduce_bf16_kernel<1>, 256, (size_t)smem);
+  bf16_col_cfg(R, C, g8, rpc, smem, slots);
+  colreduce_bf16_kernel<1><<<g8, 256, smem, st>>>((const bf16 *)dy_bf16, (const bf16 *)x_bf16, scale, shift, mean, rstd, relu, red, red + C, nullptr, R, C, rpc);
+  VPF_TRY(check_launch("colreduce_bf16_kernel<1>"));
+  float *fm = reinterpret_cast<float *>(red + 2 * C);
+  bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, fm, dgamma, dbeta, R, C);
+  VPF_TRY(check_launch("bn_bwd_means_kernel"));
+  VPF_RESIDENT_CTAS(slots2, bn_bwd_apply_gsum_kernel, 256, 0);
+  const long long G = R / S;
+  const int grid = (int)min((long long)slots2, ceil_div(G, 8LL));
+  bn_bwd_apply_gsum_kernel<<<grid, 256, 0, st>>>((const bf16 *)dy_bf16, (const bf16 *)x_bf16, scale, shift, mean, rstd, relu, fm, (bf16 *)dx_bf16, (bf16 *)gsum_bf16, gsum_f32, G, S);
+  return check_launch("bn_bwd_apply_gsum_kernel");
 }
 
 int vpf_gelu_fwd(const void *z_bf16, void *h_bf16, long long n, void *stream) {

@@ -192,12 +192,12 @@ def group2emb_bwd(dtok, c, W, G, cfg):
     dh3 = _empty((R, 256), BF16, dtok)
     _dgrad(dy4, W.w4, dh3)
     del dy4
-    dy3 = ops.bn_backward(dh3, c.y3, c.st3, True, G.bn3_w, G.bn3_b)
+    # BatchNorm backward and the per-patch row sum of its result (for the per-patch half of the split conv3) in one pass
+    dy3, dug, _ = ops.bn_backward_gsum(dh3, c.y3, c.st3, True, G.bn3_w, G.bn3_b, S)
     del dh3
     _wgrad(dy3, c.f2, G.w3[:, 128:])
     df2 = _empty((R, 128), BF16, dtok)
     _dgrad(dy3, W.w3[:, 128:], df2)
-    dug, _ = ops.group_sum(dy3, Gt, S, 256)
     del dy3
     ops.colsum(dug, sum32=G.b3)
     _wgrad(dug, c.gmax, G.w3[:, :128])

@@ -237,6 +237,21 @@ def bn_backward(dy, x, st, relu, dgamma, dbeta, out_dtype=BF16):
     return dx
 
 
+def bn_backward_gsum(dy, x, st, relu, dgamma, dbeta, S, want_bf16=True, want_f32=False):
+    """bn_backward of an all-bf16 [R, 256] tensor + the sum of dx over groups of S consecutive rows, one pass.
+    -> (dx bf16 [R, 256], gsum bf16 [R/S, 256] or None, gsum fp32 or None)."""
+    if not st.training:
+        raise NotImplementedError("backward through an eval-mode BatchNorm1d (running statistics) is not built")
+    R, C = x.shape
+    red = torch.empty(_ws("vpf_bn_bwd_workspace_bytes", C) // 8, dtype=torch.float64, device=x.device)
+    dx = torch.empty((R, C), dtype=BF16, device=x.device)
+    gb = torch.empty((R // S, C), dtype=BF16, device=x.device) if want_bf16 else None
+    gf = torch.empty((R // S, C), dtype=F32, device=x.device) if want_f32 else None
+    _lib.call("vpf_bn_bwd_gsum", _p(dy), _p(x), _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd), _i(int(relu)), _p(red),
+              _p(dx), _p(dgamma), _p(dbeta), _ll(R), _i(C), _i(S), _p(gb), _p(gf), _s())
+    return dx, gb, gf
+
+
 # ----------------------------------------------------------------------------- pooling / thin ops
 def group_max_fwd(x, G, S, C, want_bf16=True, want_f32=False):
     ob = torch.empty((G, C), dtype=BF16, device=x.device) if want_bf16 else None
