@@ -61,11 +61,15 @@ for T in (65536, 36864):
         "ln_fwd": (T * D * 6, lambda: ops.layernorm_fwd(x, gam, bet)),
         "ln_fwd_add": (T * D * 10, lambda: ops.layernorm_fwd(x, gam, bet, add=pos, want_xsum=True)),
         "ln_bwd": (T * D * 14, lambda: ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dgam, dbeta=dbet)),
+        "ln_bwd_nodg": (T * D * 14, lambda: ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres)),
         "ln_bwd_pos": (T * D * 14, lambda: ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dgam, dbeta=dbet, dpos=dpos)),
         "gelu_fwd": (T * Fh * 4, lambda: ops.gelu_fwd(z)),
         "gelu_bwd": (T * Fh * 6, lambda: ops.gelu_bwd(dh, z, colsum=cs)),
         "dropout_grad": (T * D * 6, lambda: ops.dropout_grad(dres, 0.5, seed, 7, colsum=cs2)),
     }
+    # yardstick: a plain device copy of the same total traffic (torch's copy kernel; what this size can reach at all)
+    ca, cb2 = torch.empty(T * D * 7, dtype=torch.uint8, device="cuda"), torch.empty(T * D * 7, dtype=torch.uint8, device="cuda")
+    cases["copy(=ln_bwd bytes)"] = (2 * ca.numel(), lambda: cb2.copy_(ca))
     for name, (nb, fn) in cases.items():
         if which and name not in which:
             continue
