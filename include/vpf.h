@@ -182,6 +182,14 @@ int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, co
                       const float *mean, const float *rstd, const float *gamma, const float *dres,
                       void *dx, int dx_bf16, float *dgamma, float *dbeta, float *dpos, int pos_rows,
                       int T, int D, void *stream);
+/* vpf_layernorm_bwd for (bf16 dy, fp32 x, fp32 dx, D % 128 == 0) that ALSO emits g_bf16 = dropout_mask(dx) * scale
+ * (the byte-granular Residual mask of (seed, op_id), drop_p = 0 -> plain bf16 copy) and accumulates its column sums
+ * into g_colsum (optional): the operand / bias gradient of the next block down the backward chain (partseg.py:208-213),
+ * which otherwise costs a separate vpf_dropout_grad pass over dx. */
+int vpf_layernorm_bwd_emit(const void *dy_bf16, const float *x, const float *mean, const float *rstd,
+                           const float *gamma, const float *dres, float *dx, float *dgamma, float *dbeta,
+                           float *dpos, int pos_rows, int T, int D, void *g_bf16, float *g_colsum, float drop_p,
+                           const unsigned long long *seed_ptr, unsigned int op_id, void *stream);
 /* Residual.dropout backward (partseg.py:201-213): out_bf16 = mask(g)/(1-p); colsum += column sums. */
 int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p,
                      const unsigned long long *seed_ptr, unsigned int op_id, int T, int N, void *stream);

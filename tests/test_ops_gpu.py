@@ -257,6 +257,36 @@ def test_residual_dropout_mask_equals_the_oracle_restatement(T, N, p):
     assert abs((m != 0).float().mean().item() - (1 - R.threshold8(p) / 256)) < 0.02
 
 
+@pytest.mark.parametrize("T,D,pos_rows,p", [(4096, 256, 128, 0.5), (1152, 384, 144, 0.1), (1000, 256, 0, 0.0), (77, 128, 0, 0.5)])
+def test_layernorm_backward_emit_equals_two_kernels(T, D, pos_rows, p):
+    """vpf_layernorm_bwd_emit == vpf_layernorm_bwd followed by vpf_dropout_grad: same dx, same masked bf16 copy (bit for
+    bit: same mask stream), same bias column sums, same dgamma / dbeta / dpos."""
+    from vipformer_b200 import ops
+
+    x, dres = rnd((T, D), 1), rnd((T, D), 2)
+    dy = rnd((T, D), 3, BF16)
+    gam = rnd((D,), 4) * 0.2 + 1.0
+    _, mean, rstd, _ = ops.layernorm_fwd(x, gam, torch.zeros(D, device="cuda"))
+    seed = torch.tensor([99 + T], device="cuda", dtype=torch.int64)
+
+    def z(*shape):
+        return torch.zeros(shape, device="cuda")
+
+    dg0, db0, cs0 = z(D), z(D), z(D)
+    dp0 = z(pos_rows, D) if pos_rows else None
+    dx0 = ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dg0, dbeta=db0, dpos=dp0)
+    g0 = ops.dropout_grad(dx0, p, seed, 21, colsum=cs0)
+    dg1, db1, cs1 = z(D), z(D), z(D)
+    dp1 = z(pos_rows, D) if pos_rows else None
+    dx1, g1 = ops.layernorm_bwd_emit(dy, x, mean, rstd, gam, (p, seed, 21, cs1), dres=dres, dgamma=dg1, dbeta=db1, dpos=dp1)
+    assert torch.equal(dx1, dx0) and torch.equal(g1, g0)
+    close(cs1, cs0, tol=1e-5)
+    close(dg1, dg0, tol=1e-5)
+    close(db1, db0, tol=1e-5)
+    if pos_rows:
+        close(dp1, dp0, tol=1e-5)
+
+
 @pytest.mark.parametrize("G,S", [(300, 32), (17, 8), (5, 33)])
 def test_bn_backward_fused_group_sum(G, S):
     """vpf_bn_bwd_gsum == vpf_bn_bwd followed by vpf_group_sum (Group2Emb backward), dgamma / dbeta included."""

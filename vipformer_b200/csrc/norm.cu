@@ -190,14 +190,36 @@ ln_fwd_rows_kernel(const Tin *__restrict__ x, const float *__restrict__ add, int
 // ------------------------------------------------------------- LayerNorm bwd
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = gamma * dy  (dy masked by y > 0 when relu)
 // dx_out = dres + dx;  dpos[row % pos_rows] += dx_out;  dgamma += sum dy*xhat;  dbeta += sum dy
-template <typename Tdy, typename Tx, typename Tdx, int NPER, bool VEC>
+// EMIT: the kernel also writes g = bf16(dropout_mask(dx_out) * scale) and accumulates its column sums -- the masked copy
+// of the residual-stream gradient that the NEXT block down the backward chain needs as a GEMM operand (Residual,
+// partseg.py:208-213: d/d(branch output) = mask * dx, bias gradient = its column sum).  That used to be a separate
+// pass over dx (dropout_grad); with one hash per four elements and this kernel at ~20 % issue utilisation it rides along.
+struct LnEmit {
+  __nv_bfloat16 *g;
+  float *colsum;
+  const unsigned long long *seed;
+  uint32_t op_id;
+  float p;
+};
+template <typename Tdy, typename Tx, typename Tdx, int NPER, bool VEC, bool EMIT = false>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_bfloat16 *__restrict__ y_relu,
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in, const float *__restrict__ gamma,
               const float *__restrict__ dres, Tdx *__restrict__ dx, float *__restrict__ dgamma,
-              float *__restrict__ dbeta, float *__restrict__ dpos, int pos_rows, int T, int rows_per_cta) {
+              float *__restrict__ dbeta, float *__restrict__ dpos, int pos_rows, int T, int rows_per_cta, LnEmit em) {
   constexpr int D = NPER * 32;
+  static_assert(!EMIT || VEC, "the emitting variant exists for the vector layout only");
   __shared__ float s_dg[D], s_db[D];
+  uint32_t em_thr = 0, em_key = 0;
+  float em_scale = 1.f;
+  float gs[EMIT ? NPER : 1];
+  if constexpr (EMIT) {
+    em_thr = rng::threshold8(em.p);
+    em_key = em_thr ? rng::make_key(em.seed ? *em.seed : 0ull, em.op_id) : 0u;
+    em_scale = rng::scale8(em_thr);
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) gs[i] = 0.f;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float dg[NPER], db[NPER], gm[NPER];
   // element i of this lane lives at column col(i)
@@ -281,6 +303,12 @@ ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_b
         const int c = (lane + 32 * q) * 4;
         const float4 o = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
         st4<Tdx>(dx, base + c, o);
+        if constexpr (EMIT) {
+          float f[4] = {o.x, o.y, o.z, o.w};
+          if (em_thr) rng::drop_values<4>(f, em_key, (uint32_t)(base + c), em_thr, em_scale, true);
+          st4<__nv_bfloat16>(em.g, base + c, make_float4(f[0], f[1], f[2], f[3]));
+          gs[4 * q] += f[0]; gs[4 * q + 1] += f[1]; gs[4 * q + 2] += f[2]; gs[4 * q + 3] += f[3];
+        }
         if (dpos) {
           if (!tok_major) {
             float4 pp = ld4<float>(dpos, base + c);
@@ -316,6 +344,17 @@ ln_bwd_kernel(const Tdy *__restrict__ dy, const Tx *__restrict__ x, const __nv_b
     for (int c = threadIdx.x; c < D; c += 256) {
       atomicAdd(dgamma + c, s_dg[c]);
       atomicAdd(dbeta + c, s_db[c]);
+    }
+  }
+  if constexpr (EMIT) {
+    if (em.colsum) {
+      __syncthreads();
+      for (int c = threadIdx.x; c < D; c += 256) s_dg[c] = 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) atomicAdd(&s_dg[col(i)], gs[i]);
+      __syncthreads();
+      for (int c = threadIdx.x; c < D; c += 256) atomicAdd(em.colsum + c, s_dg[c]);
     }
   }
 }
@@ -902,20 +941,27 @@ int vpf_layernorm_fwd(const void *x, int x_bf16, const float *add, int add_rows,
   return check_launch("ln_fwd_kernel");
 }
 
-int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const void *y_relu, const float *mean,
-                      const float *rstd, const float *gamma, const float *dres, void *dx, int dx_bf16, float *dgamma,
-                      float *dbeta, float *dpos, int pos_rows, int T, int D, void *stream) {
+static int layernorm_bwd_impl(const void *dy, int dy_bf16, const void *x, int x_bf16, const void *y_relu, const float *mean,
+                              const float *rstd, const float *gamma, const float *dres, void *dx, int dx_bf16, float *dgamma,
+                              float *dbeta, float *dpos, int pos_rows, int T, int D, const LnEmit *emit, void *stream) {
   VPF_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
   VPF_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be given or both null");
   if (T == 0) return VPF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tok_major = dpos && pos_rows < T;
   if (tok_major) VPF_REQUIRE(pos_rows > 0 && T % pos_rows == 0, "layernorm_bwd: T=%d is not a multiple of pos_rows=%d", T, pos_rows);
+  LnEmit em{nullptr, nullptr, nullptr, 0u, 0.f};
+  if (emit) {
+    em = *emit;
+    VPF_REQUIRE(em.g && dy_bf16 && !x_bf16 && !dx_bf16 && D % 128 == 0 && !y_relu,
+                "layernorm_bwd_emit: needs bf16 dy, fp32 x / dx, D %% 128 == 0 (D=%d)", D);
+    VPF_REQUIRE(em.p >= 0.f && em.p < 1.f && (size_t)T * (size_t)D < (1ull << 32), "layernorm_bwd_emit: p=%f or index space out of range", em.p);
+  }
   // grid = the resident set (a partial second wave cost a third of the bandwidth).  Token-major order (see the kernel):
   // warps = pos_rows * nchunk, every (token, batch-chunk) pair one warp
-#define LNB_CALL(TDY, TX, TDX, NP, VEC)                                                                               \
+#define LNB_LAUNCH(KERNEL)                                                                                            \
   {                                                                                                                   \
-    VPF_RESIDENT_CTAS(slots, (ln_bwd_kernel<TDY, TX, TDX, NP, VEC>), 256, 0);                                          \
+    VPF_RESIDENT_CTAS(slots, (KERNEL), 256, 0);                                                                       \
     int grid = min(ceil_div(T, 8), slots);                                                                            \
     const int rows_per_cta = ceil_div(T, grid);                                                                       \
     grid = ceil_div(T, rows_per_cta);                                                                                 \
@@ -923,11 +969,24 @@ int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, co
       const int nchunk = max(1, min(T / pos_rows, (slots * 8) / pos_rows));                                           \
       grid = ceil_div(pos_rows * nchunk, 8);                                                                          \
     }                                                                                                                 \
-    ln_bwd_kernel<TDY, TX, TDX, NP, VEC><<<grid, 256, 0, st>>>((const TDY *)dy, (const TX *)x, (const bf16 *)y_relu, mean, rstd, gamma, dres, \
-                                                           (TDX *)dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta); \
+    KERNEL<<<grid, 256, 0, st>>>((decltype(lnb_dy))dy, (decltype(lnb_x))x, (const bf16 *)y_relu, mean, rstd, gamma, dres,  \
+                                 (decltype(lnb_dx))dx, dgamma, dbeta, dpos, pos_rows, T, rows_per_cta, em);          \
+  }
+#define LNB_CALL(TDY, TX, TDX, NP, VEC)                                                                               \
+  {                                                                                                                   \
+    const TDY *lnb_dy = nullptr; const TX *lnb_x = nullptr; TDX *lnb_dx = nullptr;                                    \
+    (void)lnb_dy; (void)lnb_x; (void)lnb_dx;                                                                          \
+    LNB_LAUNCH((ln_bwd_kernel<TDY, TX, TDX, NP, VEC, false>))                                                         \
+  }
+#define LNB_CALL_EMIT(NP)                                                                                             \
+  {                                                                                                                   \
+    const bf16 *lnb_dy = nullptr; const float *lnb_x = nullptr; float *lnb_dx = nullptr;                              \
+    (void)lnb_dy; (void)lnb_x; (void)lnb_dx;                                                                          \
+    LNB_LAUNCH((ln_bwd_kernel<bf16, float, float, NP, true, true>))                                                   \
   }
 #define LNB(NP, VEC)                                                                     \
-  if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP, VEC)                  \
+  if (emit) { if (VEC) LNB_CALL_EMIT(NP >= 4 ? NP : 4) }                                 \
+  else if (dy_bf16 && x_bf16 && dx_bf16) LNB_CALL(bf16, bf16, bf16, NP, VEC)             \
   else if (dy_bf16 && !x_bf16 && dx_bf16) LNB_CALL(bf16, float, bf16, NP, VEC)           \
   else if (!dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(float, float, float, NP, VEC)       \
   else if (dy_bf16 && !x_bf16 && !dx_bf16) LNB_CALL(bf16, float, float, NP, VEC)         \
@@ -936,7 +995,26 @@ int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, co
   LN_DISPATCH(D, LNB)
 #undef LNB
 #undef LNB_CALL
+#undef LNB_CALL_EMIT
+#undef LNB_LAUNCH
   return check_launch("ln_bwd_kernel");
+}
+
+int vpf_layernorm_bwd(const void *dy, int dy_bf16, const void *x, int x_bf16, const void *y_relu, const float *mean,
+                      const float *rstd, const float *gamma, const float *dres, void *dx, int dx_bf16, float *dgamma,
+                      float *dbeta, float *dpos, int pos_rows, int T, int D, void *stream) {
+  return layernorm_bwd_impl(dy, dy_bf16, x, x_bf16, y_relu, mean, rstd, gamma, dres, dx, dx_bf16, dgamma, dbeta, dpos, pos_rows,
+                            T, D, nullptr, stream);
+}
+
+int vpf_layernorm_bwd_emit(const void *dy_bf16, const float *x, const float *mean, const float *rstd, const float *gamma,
+                           const float *dres, float *dx, float *dgamma, float *dbeta, float *dpos, int pos_rows, int T, int D,
+                           void *g_bf16, float *g_colsum, float drop_p, const unsigned long long *seed_ptr,
+                           unsigned int op_id, void *stream) {
+  VPF_REQUIRE(g_bf16, "layernorm_bwd_emit: null pointer");
+  const LnEmit em{(__nv_bfloat16 *)g_bf16, g_colsum, seed_ptr, op_id, drop_p};
+  return layernorm_bwd_impl(dy_bf16, 1, x, 0, nullptr, mean, rstd, gamma, dres, dx, 0, dgamma, dbeta, dpos, pos_rows, T, D, &em,
+                            stream);
 }
 
 int vpf_dropout_grad(const float *g, void *out_bf16, float *colsum, float p, const unsigned long long *seed_ptr,

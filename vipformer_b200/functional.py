@@ -32,6 +32,9 @@ def _dgrad(dy, w, out, **kw):
     return ops.gemm(dy, w, out, b_mn=True, **kw)
 
 
+_EMIT = __import__("os").environ.get("VPF_LN_EMIT", "1") != "0"   # measurement switch: LayerNorm backward emits the next operand
+
+
 # =============================================================================== MLP (partseg.py:191-198)
 def _mlp_fwd(x1, W, T, D, p_drop, seed, op_id, save):
     xn2, mean2, rstd2, _ = ops.layernorm_fwd(x1, W.ln2_w, W.ln2_b)
@@ -47,8 +50,18 @@ def _mlp_fwd(x1, W, T, D, p_drop, seed, op_id, save):
     return x2, NS(xn2=xn2, mean2=mean2, rstd2=rstd2, h=h, z=z, x1=x1)
 
 
-def _mlp_bwd(dx2, c, W, G, T, D, p_drop, seed, op_id):
-    g2 = ops.dropout_grad(dx2, p_drop, seed, op_id, colsum=G.b2)
+def _ln_bwd(dy, x, mean, rstd, gamma, emit, **kw):
+    """LayerNorm backward; with `emit` = (drop_p, seed, op_id, colsum) also the masked bf16 copy of the result that the next
+    block down the chain consumes (ops.layernorm_bwd_emit) -> (dx, g or None)."""
+    if emit is not None and _EMIT and ops.can_emit(dy, x, x.shape[1]):
+        return ops.layernorm_bwd_emit(dy, x, mean, rstd, gamma, emit, **kw)
+    return ops.layernorm_bwd(dy, x, mean, rstd, gamma, **kw), None
+
+
+def _mlp_bwd(dx2, c, W, G, T, D, p_drop, seed, op_id, g2=None, emit=None):
+    """g2: the masked bf16 copy of dx2 when the block above already produced it; emit: what to produce for the block below."""
+    if g2 is None:
+        g2 = ops.dropout_grad(dx2, p_drop, seed, op_id, colsum=G.b2)
     _wgrad(g2, c.h, G.w2)
     F_ = W.w1.shape[0]
     dh = _empty((T, F_), BF16, dx2)
@@ -57,7 +70,7 @@ def _mlp_bwd(dx2, c, W, G, T, D, p_drop, seed, op_id):
     _wgrad(dz, c.xn2, G.w1)
     dxn2 = _empty((T, D), BF16, dx2)      # gradient w.r.t. the LayerNorm output: a bf16 operand like dh / dz / dqkv
     _dgrad(dz, W.w1, dxn2)
-    return ops.layernorm_bwd(dxn2, c.x1, c.mean2, c.rstd2, W.ln2_w, dres=dx2, dgamma=G.ln2_w, dbeta=G.ln2_b)
+    return _ln_bwd(dxn2, c.x1, c.mean2, c.rstd2, W.ln2_w, emit, dres=dx2, dgamma=G.ln2_w, dbeta=G.ln2_b)
 
 
 # ============================================================ SelfAttentionLayer (partseg.py:170-188)
@@ -76,11 +89,15 @@ def sa_layer_fwd(x_prev, pos, W, cfg, seed, op_base, save=True):
     return x2, ctx
 
 
-def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos):
+def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, g2=None, emit=None):
+    """-> (dx, g): g = masked bf16 copy of dx for the layer below when `emit` = (drop_p, seed, op_id, colsum) asks for it.
+    The LayerNorm backward of the MLP block emits this layer's own attention-residual operand (g1) the same way."""
     B, L, D, H = cfg.B, cfg.L, cfg.D, cfg.H
     T = B * L
-    dx1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2)
-    g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
+    dx1, g1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2, g2=g2,
+                       emit=(cfg.p_res1, seed, op_base + 1, G.bo))
+    if g1 is None:
+        g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
     _wgrad(g1, c.o, G.wo)
     do = _empty((T, D), BF16, dx2)
     _dgrad(g1, W.wo, do)
@@ -91,7 +108,7 @@ def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos):
     _wgrad(dqkv, c.xn, G.wqkv)
     dxn = _empty((T, D), BF16, dx2)
     _dgrad(dqkv, W.wqkv, dxn)
-    return ops.layernorm_bwd(dxn, c.xin, c.mean1, c.rstd1, W.ln1_w, dres=dx1, dgamma=G.ln1_w, dbeta=G.ln1_b, dpos=dpos)
+    return _ln_bwd(dxn, c.xin, c.mean1, c.rstd1, W.ln1_w, emit, dres=dx1, dgamma=G.ln1_w, dbeta=G.ln1_b, dpos=dpos)
 
 
 # =========================================================== CrossAttentionLayer (partseg.py:144-167)
@@ -114,11 +131,13 @@ def ca_layer_fwd(xq_prev, pos, kv_in, W, cfg, seed, op_base, save=True):
     return x2, ctx
 
 
-def ca_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, need_dkv=True):
+def ca_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, need_dkv=True, g2=None):
     B, L, Lk, D, H = cfg.B, cfg.L, cfg.Lk, cfg.D, cfg.H
     T, Tk = B * L, B * Lk
-    dx1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2)
-    g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
+    dx1, g1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2, g2=g2,
+                       emit=(cfg.p_res1, seed, op_base + 1, G.bo))
+    if g1 is None:
+        g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
     _wgrad(g1, c.o, G.wo)
     do = _empty((T, D), BF16, dx2)
     _dgrad(g1, W.wo, do)

@@ -312,16 +312,24 @@ class _EncoderFn(torch.autograd.Function):
         if ctx.has_pos:
             dpos = ops.zeros_(torch.empty(ctx.pos_shape, dtype=F32, device=dev))
         dkv = None
+        g = None     # masked bf16 copy of dx, emitted by the layer above for this layer's MLP residual (functional._ln_bwd)
         for li in range(len(ctx.ctxs) - 1, -1, -1):
             layer, cfg, c, op_base = ctx.ctxs[li]
             if li in tap_grads:
                 dx = tap_grads[li] if dx is None else ops.add_scale(dx, tap_grads[li], 1.0)
+                g = None         # a tap gradient joined the stream here: the emitted copy no longer matches dx
             if dx is None:       # nothing flows into this layer (no tap at or behind it)
                 continue
+            G = layer._grads()
             if isinstance(layer, CrossAttentionLayer):
-                dx, dkv = Fn.ca_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, op_base, dpos)
+                dx, dkv = Fn.ca_layer_bwd(dx, c, layer._weights(), G, cfg, ctx.seed, op_base, dpos, g2=g)
+                g = None
             else:
-                dx = Fn.sa_layer_bwd(dx, c, layer._weights(), layer._grads(), cfg, ctx.seed, op_base, dpos)
+                emit = None
+                if li > 0 and (li - 1) not in tap_grads:       # the layer below consumes dx through its MLP-residual dropout
+                    below, cfg_b, _, op_b = ctx.ctxs[li - 1]
+                    emit = (cfg_b.p_res2, ctx.seed, op_b + 2, below._grads().b2)
+                dx, g = Fn.sa_layer_bwd(dx, c, layer._weights(), G, cfg, ctx.seed, op_base, dpos, g2=g, emit=emit)
         ctx.ctxs = None
         if dkv is not None:
             dkv = dkv.view(ctx.kv_shape)

@@ -184,6 +184,23 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, y_relu=None, dres=None, dgamma=No
     return dx
 
 
+def layernorm_bwd_emit(dy, x, mean, rstd, gamma, emit, *, dres=None, dgamma=None, dbeta=None, dpos=None):
+    """layernorm_bwd (bf16 dy, fp32 x -> fp32 dx) that also returns g = bf16(dropout_mask(dx)) for the next block down the
+    chain.  emit = (drop_p, seed, op_id, colsum or None).  -> (dx fp32, g bf16)."""
+    T, D = x.shape
+    p_drop, seed, op_id, colsum = emit
+    dx = torch.empty((T, D), dtype=F32, device=x.device)
+    g = torch.empty((T, D), dtype=BF16, device=x.device)
+    pos_rows = 0 if dpos is None else dpos.numel() // D
+    _lib.call("vpf_layernorm_bwd_emit", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dgamma), _p(dbeta),
+              _p(dpos), _i(pos_rows), _i(T), _i(D), _p(g), _p(colsum), _f(p_drop), _p(seed), _u(op_id), _s())
+    return dx, g
+
+
+def can_emit(dy, x, D):
+    return dy.dtype == BF16 and x.dtype == F32 and D % 128 == 0 and x.numel() < (1 << 32)
+
+
 def dropout_grad(g, p, seed, op_id, colsum=None):
     T, N = g.shape
     out = torch.empty((T, N), dtype=BF16, device=g.device)
