@@ -368,7 +368,7 @@ def run_ours(args):
         phase("teardown")
         dist.barrier()
         torch.cuda.synchronize()
-        eng.graph = None
+        eng.close()
         del eng
         torch.cuda.synchronize()
         dist.destroy_process_group()

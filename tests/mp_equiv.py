@@ -22,6 +22,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _say(rank, msg):
+    if os.environ.get("VPF_MP_VERBOSE"):
+        print(f"[mp_equiv rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -52,6 +57,7 @@ def main():
     rel = lambda a, r: ((a.detach().double().cpu() - r).norm() / r.norm()).item()
     assert rel(pc_local.grad, gref_pc) < 1e-4 and rel(im_local.grad, gref_im) < 1e-4, (rel(pc_local.grad, gref_pc), rel(im_local.grad, gref_im))
 
+    _say(rank, "loss level ok")
     # ---------------------------------------------------------------- (2) engine level
     cfg = _synth.MODEL_CASES["small"]
     results = {}
@@ -62,8 +68,11 @@ def main():
         gg = torch.Generator().manual_seed(50 + rank)          # different data per rank
         eng.pc_in.copy_((torch.randn((2 * cfg["b"], cfg["N"], 3), generator=gg) * 0.4).cuda())
         eng.img_in.copy_(torch.randn((cfg["b"], 3, 144, 144), generator=gg).cuda())
-        hist = [eng.step().clone() for _ in range(3)]
-        torch.cuda.synchronize()
+        hist = []
+        for i in range(3):
+            hist.append(eng.step().clone())
+            torch.cuda.synchronize()
+            _say(rank, f"graph={graph} step {i} done")
         assert all(torch.isfinite(h).all() for h in hist)
         p = eng.arena.flat_p
         p0 = p.clone()
@@ -75,6 +84,7 @@ def main():
         assert torch.equal(gsum, g0), "all-reduced gradients differ across ranks"
         assert eng.state[0].item() == 3
         results[graph] = (torch.stack(hist).cpu(), p.clone())
+        eng.close()
     # eager vs graph: same seeds, same data; the only differences are fp32 atomics order
     h0, h1 = results[False][0], results[True][0]
     assert torch.allclose(h0[0], h1[0], rtol=1e-3, atol=1e-3), (h0, h1)
@@ -83,7 +93,7 @@ def main():
         print(f"MP_EQUIV_OK world={world} loss={mean_loss.cpu().tolist()} engine_losses={h0[-1].tolist()}", flush=True)
     # tear-down: the CUDA graph holds captured NCCL kernels -- drop it (and the engines) before the communicator
     torch.cuda.synchronize()
-    del eng, results
+    del eng, results, pc, img
     import gc
     gc.collect()
     torch.cuda.synchronize()

@@ -197,5 +197,5 @@ def test_multi_gpu_equivalence_over_nccl():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(root, "tests", "mp_equiv.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "MP_EQUIV_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -13,6 +13,7 @@ B200-first structure:
   * GradScaler (pretrain.py:154,209-211) is dropped: bf16 operands with fp32 accumulation need no loss scaling.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -96,10 +97,24 @@ class PretrainEngine:
         self._img_after_g2e = self.side is not None and os.environ.get("VPF_IMG_AFTER_G2E", "1") != "0"
         if self._img_after_g2e:
             self._g2e_done = None      # armed only inside _step_body: the hook is inert when the model is called on its own
-            self.pc_model.group2emb.register_forward_hook(lambda m, i, o: self._g2e_done.record() if self._g2e_done is not None else None)
+            me = weakref.ref(self)     # the module must not keep the engine (and its CUDA graph with captured NCCL kernels) alive
+
+            def _mark(module, inputs, output):
+                eng = me()
+                if eng is not None and eng._g2e_done is not None:
+                    eng._g2e_done.record()
+
+            self._g2e_hook = self.pc_model.group2emb.register_forward_hook(_mark)
         self._copy_stream, self._staged = None, False
         self._loss_ring, self._loss_pending = None, None
         self.steps_done = 0
+
+    def close(self):
+        """Drop the captured graph (it holds NCCL kernels: do this BEFORE destroy_process_group) and the scheduling hook."""
+        self.graph = None
+        h = self.__dict__.pop("_g2e_hook", None)
+        if h is not None:
+            h.remove()
 
     # ------------------------------------------------------------------------------------------------ one step
     def set_lr(self, lr):
