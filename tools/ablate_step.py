@@ -2,6 +2,9 @@
 entries turned into no-ops (results are garbage, timing is not: no kernel on this path branches on data except the
 attention's lazy rescale), capture the step graph, time it, report baseline - ablated.  ncu's per-launch times are
 cold-cache and serialised; this is what a kernel costs inside the captured two-stream step.
+CAVEAT: the skipped kernels leave NaN garbage behind, which changes later kernels' data-dependent
+branches -- the numbers are hints for where to look, not a cost model; `--only baseline` (nothing skipped) is the reliable
+use: same-box A/B timing of a build under the VPF_* environment switches.
 
     python tools/ablate_step.py [--pairs 256] [--steps 10] [--config A]
 """

@@ -6,7 +6,7 @@
 B200-first structure:
   * both models live in ONE parameter arena: a single flat fp32 gradient buffer is zeroed by one memset, all-reduced
     by ONE NCCL call over NVLink/NVSwitch, and consumed by ONE fused AdamW kernel that also refreshes the bf16 shadows;
-  * the whole step (FPS start draw, ~600 kernel launches, collectives, optimizer) is captured in a CUDA graph and
+  * the whole step (FPS start draw, ~480 kernel launches on three streams, collectives, optimizer) is captured in a CUDA graph and
     replayed; per-step dropout seeds / step count / learning rate live in device memory so the graph stays valid;
   * with world_size > 1 NT-Xent negatives span the global batch (all-gather of normalised embeddings + of the per-row
     log-sum-exp, SURVEY.md 8e); BatchNorm statistics stay rank-local exactly like the reference (no SyncBN);
