@@ -227,6 +227,9 @@ int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, vo
                       int accumulate, int G, int S, int C, void *stream);
 /* sum over the S rows of each group (gradient of the broadcast in utils.py:183). */
 int vpf_group_sum(const void *x_bf16, void *out_bf16, float *out_f32, int G, int S, int C, void *stream);
+/* out[n] += sum_k v[k] * W[k, n] for a bf16 [K, ldw] matrix window (fp32 accumulate): colsum(dY . W) = colsum(dY) . W,
+ * the bias gradient of Group2Emb's first_conv.3 without a pass over the [B*G*S, 128] data gradient (utils.py:156). */
+int vpf_vecmat_bf16(const float *v, const void *W_bf16, int ldw, int K, int N, float *out, void *stream);
 /* cat(x.max(1)[0], x.mean(1)), partseg.py:547. */
 int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream);
 int vpf_token_pool_bwd(const float *dout, const int *argmax, float *dx, int B, int L, int D, void *stream);

@@ -569,6 +569,17 @@ __global__ void bn_fold_kernel(const float *__restrict__ W, const float *__restr
 static inline int grid_for(size_t total) { return (int)min((size_t)num_sms() * 8, ceil_div(total, (size_t)256)); }
 static inline int rows_per_cta_for(long long R) { return (int)max((long long)64, ceil_div(R, (long long)num_sms() * 8)); }
 
+// out[n] += sum_k v[k] * W[k, n]   (fp32 vector times a bf16 [K, ldw] matrix window; K, N a few hundred)
+// Group2Emb backward uses it for a bias gradient: colsum(dY . W) = colsum(dY) . W, which replaces a pass over a 0.5 GB tensor.
+__global__ void __launch_bounds__(128)
+vecmat_bf16_kernel(const float *__restrict__ v, const bf16 *__restrict__ W, int ldw, int K, int N, float *__restrict__ out) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(v[k], __bfloat162float(W[(size_t)k * ldw + n]), acc);
+  out[n] += acc;
+}
+
 }  // namespace vpf
 
 using namespace vpf;
@@ -597,6 +608,13 @@ int vpf_group_sum(const void *x_bf16, void *out_bf16, float *out_f32, int G, int
   if (G == 0 || C == 0) return VPF_OK;
   group_sum_kernel<<<dim3(G, ceil_div(C, 128)), 128, 0, (cudaStream_t)stream>>>((const bf16 *)x_bf16, (bf16 *)out_bf16, out_f32, S, C);
   return check_launch("group_sum_kernel");
+}
+
+int vpf_vecmat_bf16(const float *v, const void *W_bf16, int ldw, int K, int N, float *out, void *stream) {
+  VPF_REQUIRE(v && W_bf16 && out && ldw >= N, "vecmat_bf16: bad arguments");
+  if (K == 0 || N == 0) return VPF_OK;
+  vecmat_bf16_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(v, (const bf16 *)W_bf16, ldw, K, N, out);
+  return check_launch("vecmat_bf16_kernel");
 }
 
 int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream) {

@@ -218,12 +218,17 @@ def group2emb_bwd(dtok, c, W, G, cfg):
     df2 = _empty((R, 128), BF16, dtok)
     _dgrad(dy3, W.w3[:, 128:], df2)
     del dy3
-    ops.colsum(dug, sum32=G.b3)
+    cs3 = ops.zeros_(_empty((256,), F32, dtok))
+    ops.colsum(dug, sum32=cs3)                       # = column sums of dy3 over ALL rows (dug holds the per-patch sums)
+    ops.add_scale(G.b3, cs3, 1.0, out=G.b3)
     _wgrad(dug, c.gmax, G.w3[:, :128])
     dgmax = _empty((Gt, 128), F32, dtok)
     _dgrad(dug, W.w3[:, :128], dgmax)
     ops.group_max_bwd(dgmax, c.am2, Gt, S, 128, dx=df2)
-    ops.colsum(df2, sum32=G.b2)
+    # bias gradient of conv2 = colsum(df2) = colsum(dy3) . W3[:, 128:] + colsum(dgmax): two tiny kernels instead of a pass
+    # over the 0.5 GB df2 (and without the bf16 rounding of its entries)
+    ops.vecmat_bf16(cs3, W.w3[:, 128:], G.b2)
+    ops.colsum(dgmax, sum32=G.b2)
     _wgrad(df2, c.h1, G.w2)
     dh1 = _empty((R, 64), BF16, dtok)
     _dgrad(df2, W.w2, dh1)

@@ -293,6 +293,14 @@ def group_sum(x, G, S, C, want_bf16=True, want_f32=False):
     return ob, of
 
 
+def vecmat_bf16(v, W, out):
+    """out[n] += sum_k v[k] * W[k, n];  v fp32 [K], W bf16 [K, N] window (row stride W.stride(0)), out fp32 [N]."""
+    K, N = W.shape
+    assert v.dtype == F32 and W.dtype == BF16 and out.dtype == F32 and v.numel() == K and out.numel() == N and W.stride(1) == 1
+    _lib.call("vpf_vecmat_bf16", _p(v), _p(W), _i(W.stride(0)), _i(K), _i(N), _p(out), _s())
+    return out
+
+
 def token_pool_fwd(x, B, L, D):
     out = torch.empty((B, 2 * D), dtype=F32, device=x.device)
     am = torch.empty((B, D), dtype=torch.int32, device=x.device)
