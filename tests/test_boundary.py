@@ -57,3 +57,18 @@ def test_cpu_tensors_are_rejected_loudly():
 
     with pytest.raises(_lib.VpfError):
         divide_patches(torch.randn(1, 64, 3), 8, 4)
+
+
+def test_every_exported_symbol_is_declared_in_the_header():
+    """The reverse of the export check: nothing reachable in the .so is missing from include/vpf.h."""
+    import re
+    import subprocess
+
+    from vipformer_b200 import _lib
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
+    syms = sorted({l.split()[-1] for l in out.splitlines() if re.search(r"\bT vpf_", l)})
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vpf.h")).read()
+    assert len(syms) > 50
+    missing = [s for s in syms if not re.search(r"\b" + s + r"\s*\(", hdr)]
+    assert not missing, missing
