@@ -227,6 +227,12 @@ int vpf_group_max_bwd(const void *dout, int dout_bf16, const uint8_t *argmax, vo
                       int accumulate, int G, int S, int C, void *stream);
 /* sum over the S rows of each group (gradient of the broadcast in utils.py:183). */
 int vpf_group_sum(const void *x_bf16, void *out_bf16, float *out_f32, int G, int S, int C, void *stream);
+/* DropPath of the reference's Residual (partseg.py:201-213, timm DropPath: per-sample keep, survivors / (1 - p)):
+ * scales[b] for one Residual from the device step seed and a site id; row_scale applies them to a [B*L, D] fp32 token
+ * matrix (out may alias x).  Note the reference drops the WHOLE sum dropout(f(x)) + x, skip connection included. */
+int vpf_droppath_scales(const unsigned long long *seed_ptr, unsigned int op_id, float p, int B, float *scales,
+                        void *stream);
+int vpf_row_scale(const float *x, const float *scales, int L, float *out, long long T, int D, void *stream);
 /* out[n] += sum_k v[k] * W[k, n] for a bf16 [K, ldw] matrix window (fp32 accumulate): colsum(dY . W) = colsum(dY) . W,
  * the bias gradient of Group2Emb's first_conv.3 without a pass over the [B*G*S, 128] data gradient (utils.py:156). */
 int vpf_vecmat_bf16(const float *v, const void *W_bf16, int ldw, int K, int N, float *out, void *stream);

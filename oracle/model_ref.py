@@ -106,9 +106,11 @@ _DROP = None
 
 
 class dropout:
-    def __init__(self, seed, op_bases, atten_drop, mlp_drop):
-        """op_bases: {"pc.encoder.cross_attn_1": id, "pc.encoder.sa_layers.0": id, ..., "img...."} (the product's)."""
-        self.cfg = dict(seed=int(seed), op_bases=op_bases, atten_drop=float(atten_drop), mlp_drop=float(mlp_drop))
+    def __init__(self, seed, op_bases, atten_drop, mlp_drop, drop_path=None):
+        """op_bases: {"pc.encoder.cross_attn_1": id, "pc.encoder.sa_layers.0": id, ..., "img...."} (the product's).
+        drop_path: {layer key (as in op_bases): DropPath rate} -- per-sample scales of oracle/rng.py droppath_scales."""
+        self.cfg = dict(seed=int(seed), op_bases=op_bases, atten_drop=float(atten_drop), mlp_drop=float(mlp_drop),
+                        drop_path=dict(drop_path or {}))
 
     def __enter__(self):
         global _DROP
@@ -137,6 +139,19 @@ def _drop_resid(y, layer_key, which, p):
     B, L, D = y.shape
     m = R.residual_keep(_DROP["seed"], _DROP["op_bases"][_PREFIX[0] + layer_key] + which, p, B * L, D)
     return y * torch.from_numpy(m).view(B, L, D).to(y.dtype)
+
+
+def _drop_path(x, layer_key, which):
+    """DropPath of Residual number `which` (1 attention, 2 MLP) of a layer, partseg.py:206,212: applied to the WHOLE sum
+    dropout(f(x)) + x (the reference's quirk), one keep decision per sample, survivors / (1 - p)."""
+    if _DROP is None:
+        return x
+    p = _DROP["drop_path"].get(_PREFIX[0] + layer_key, 0.0)
+    if p <= 0.0:
+        return x
+    from . import rng as R
+    s = R.droppath_scales(_DROP["seed"], _DROP["op_bases"][_PREFIX[0] + layer_key] + 2 + which, p, x.shape[0])
+    return x * torch.from_numpy(s).view(-1, 1, 1).to(x.dtype)
 
 
 def _lin(sd, k, x, bias=True):
@@ -194,8 +209,8 @@ def sa_layer(sd, k, x, H):
     a = k + ".0.module"
     pa, pm = (_DROP["atten_drop"], _DROP["mlp_drop"]) if _DROP else (0.0, 0.0)
     xn = _ln(sd, a + ".norm", x)
-    x = _drop_resid(mha(sd, a + ".attention", xn, xn, H, k, pa), k, 1, pm) + x
-    return _drop_resid(mlp(sd, k + ".1.module", x), k, 2, pm) + x
+    x = _drop_path(_drop_resid(mha(sd, a + ".attention", xn, xn, H, k, pa), k, 1, pm) + x, k, 1)
+    return _drop_path(_drop_resid(mlp(sd, k + ".1.module", x), k, 2, pm) + x, k, 2)
 
 
 def encoder(sd, k, group_embs, pos_embs, pts_embs, H, n_sa):
@@ -351,7 +366,7 @@ def partseg_forward(sd, pts, cls_onehot, start_idx, G, S, H, n_sa, layer_idx, tr
         h = torch.cat([f0, glob.unsqueeze(1).expand(-1, N, -1).reshape(B * N, -1)], 1)           # :452
         h = F.linear(h, sd["conv1.weight"][:, :, 0], sd["conv1.bias"])
         h = _relu(_bn(sd, "bn1", h, training, running_out), "seg.relu1")
-        if _DROP is not None and training:
+        if _DROP is not None and training and "seg.dp1" in _DROP["op_bases"]:
             from . import rng as R
             m = R.residual_keep(_DROP["seed"], _DROP["op_bases"]["seg.dp1"], 0.5, B * N, 512)
             h = h * torch.from_numpy(m).to(h.dtype)

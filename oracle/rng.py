@@ -74,3 +74,17 @@ def draw_indices(seed, op_id, n, N):
     i = np.arange(n, dtype=np.uint64)
     h = mix32(((i * np.uint64(0x9E3779B1)) & _M) ^ key)
     return ((h * np.uint64(N)) >> np.uint64(32)).astype(np.int64)
+
+
+def droppath_scales(seed, op_id, p, B):
+    """vpf_droppath_scales (pool.cu, rng.cuh keep_sample): float32 [B], 1 / (1 - p) for kept samples, 0 for dropped ones;
+    sample b is dropped iff hash(key, b) < p * 2^32."""
+    if not p > 0.0:
+        return np.ones(B, np.float32)
+    t = float(np.float32(p)) * 4294967296.0
+    thr = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+    key = np.uint64(make_key(seed, op_id))
+    b = np.arange(B, dtype=np.uint64)
+    h = mix32(((b * np.uint64(0x9E3779B1)) & _M) ^ key)
+    keep = h >= np.uint64(thr)
+    return keep.astype(np.float32) * (np.float32(1.0) / (np.float32(1.0) - np.float32(p)))   # fp32 arithmetic, as the kernel

@@ -30,10 +30,22 @@ def load():
     sys.modules.setdefault("fairscale", fs)
     sys.modules.setdefault("fairscale.nn", fsn)
 
-    class _DropPath(nn.Module):  # never executed: every shipped script has --max_dpr 0.0
+    class _DropPath(nn.Module):
+        """timm.models.layers.DropPath (timm is a requirements.txt dependency, absent here) restated from its published
+        algorithm: in training, one Bernoulli(1 - p) keep decision per SAMPLE, survivors divided by (1 - p).  The fixture
+        generator pins the draw: `scales` [B] (already 0 or 1 / (1 - p)) is assigned per instance before the forward."""
+
         def __init__(self, p=0.0):
             super().__init__()
             self.p = p
+            self.scales = None
+
+        def forward(self, x):
+            if self.p == 0.0 or not self.training:
+                return x
+            if self.scales is None:
+                raise RuntimeError("DropPath stub: assign .scales (pinned per-sample draw) before the forward")
+            return x * self.scales.to(x.dtype).view(-1, *([1] * (x.ndim - 1)))
 
     tl = types.ModuleType("timm.models.layers")
     tl.DropPath = _DropPath

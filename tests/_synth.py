@@ -122,7 +122,26 @@ SEG_CASES = {
     # part-segmentation fixtures (ft_partseg.py: 16 object classes, 50 part classes)
     "seg_small": dict(D=128, H=2, n_sa=4, G=32, S=8, N=128, MR=2, b=4, layer_idx=[1, 2, 4], parts=50, seed=71),
     "seg_cfgA": dict(D=256, H=4, n_sa=8, G=128, S=32, N=2048, MR=2, b=4, layer_idx=[2, 5, 8], parts=50, seed=72),
+    # DropPath on (the reference's own default for this model is max_dpr = 0.1): 8 samples so that several are dropped
+    "seg_small_dpr": dict(D=128, H=2, n_sa=4, G=32, S=8, N=128, MR=2, b=8, layer_idx=[1, 2, 4], parts=50, seed=73, max_dpr=0.45),
 }
+DPR_SEED = 0x5EED0D9A          # seed of the pinned DropPath draws of the fixtures (oracle/rng.py droppath_scales)
+
+
+def seg_op_bases(cfg):
+    """Dropout / DropPath site ids the fixtures and the oracle use for the part-segmentation encoder: layer i -> 8 (i + 2)."""
+    ob = {"seg.encoder.cross_attn_1": 8}
+    for i in range(cfg["n_sa"]):
+        ob[f"seg.encoder.sa_layers.{i}"] = 8 * (i + 2)
+    return ob
+
+
+def seg_drop_path(cfg):
+    """{layer key: DropPath rate}: torch.linspace(0, max_dpr, n_sa) as partseg.py:372 does."""
+    import torch
+
+    rates = [x.item() for x in torch.linspace(0, cfg.get("max_dpr", 0.0), cfg["n_sa"])]
+    return {f"seg.encoder.sa_layers.{i}": r for i, r in enumerate(rates) if r > 0.0}
 
 
 def build_seg_model(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
@@ -138,8 +157,8 @@ def build_seg_model(cfg, atten_drop=0.0, mlp_drop=0.0, pkg="vipformer_b200"):
     return part.CrossFormer_partseg(input_adapter=ad, num_latents=cfg["G"], num_latent_channels=cfg["D"], group_size=cfg["S"],
                                     num_cross_attention_layers=1, num_cross_attention_heads=cfg["H"],
                                     num_self_attention_layers=cfg["n_sa"], num_self_attention_heads=cfg["H"],
-                                    mlp_widen_factor=cfg["MR"], max_dpr=0.0, atten_drop=atten_drop, mlp_drop=mlp_drop,
-                                    layer_idx=list(cfg["layer_idx"]), num_part_classes=cfg["parts"])
+                                    mlp_widen_factor=cfg["MR"], max_dpr=cfg.get("max_dpr", 0.0), atten_drop=atten_drop,
+                                    mlp_drop=mlp_drop, layer_idx=list(cfg["layer_idx"]), num_part_classes=cfg["parts"])
 
 
 def seg_inputs(cfg):

@@ -153,6 +153,17 @@ def run_seg_case(name, cfg):
     ref.load_state_dict(_synth.perturb_state_dict(ref.state_dict(), cfg["seed"] + 10))
     ref.train()
     ref.dp1.p = 0.0          # nn.Dropout(0.5) draws from torch's RNG: off for the fixture (masks are tested on the GPU side)
+    if cfg.get("max_dpr", 0.0) > 0.0:
+        # DropPath: pin every instance's per-sample draw to oracle/rng.py droppath_scales(DPR_SEED, site id, rate)
+        from oracle import rng as R
+        ob, rates = _synth.seg_op_bases(cfg), _synth.seg_drop_path(cfg)
+        for i, layer in enumerate(ref.encoder.sa_layers):
+            key = f"seg.encoder.sa_layers.{i}"
+            for which in (1, 2):
+                dp = layer[which - 1].drop_path
+                if key in rates:
+                    assert type(dp).__name__ == "_DropPath" and abs(dp.p - rates[key]) < 1e-7
+                    dp.scales = torch.from_numpy(R.droppath_scales(_synth.DPR_SEED, ob[key] + 2 + which, rates[key], cfg["b"]))
     pts, start, onehot, labels = _synth.seg_inputs(cfg)
 
     class _T:
@@ -204,6 +215,9 @@ def main(what):
     if "seg" in what:
         for name, cfg in _synth.SEG_CASES.items():
             run_seg_case(name, cfg)
+    for w in what:                      # a single part-segmentation case: seg:<name>
+        if w.startswith("seg:"):
+            run_seg_case(w[4:], _synth.SEG_CASES[w[4:]])
 
 
 if __name__ == "__main__":

@@ -173,18 +173,28 @@ def oracle_seg_run(cfg, pins=None, drop=None, dtype=torch.float32):
                 inputs=(pts, start, onehot, labels))
 
 
-@pytest.mark.parametrize("name", ["seg_small", "seg_cfgA"])
+def seg_dpr_drop(cfg):
+    """Injection spec of the DropPath fixture: the pinned per-sample draws the fixture generator gave the reference."""
+    return dict(seed=_synth.DPR_SEED, op_bases=_synth.seg_op_bases(cfg), atten_drop=0.0, mlp_drop=0.0,
+                drop_path=_synth.seg_drop_path(cfg))
+
+
+@pytest.mark.parametrize("name", ["seg_small", "seg_cfgA", "seg_small_dpr"])
 def test_partseg_oracle_matches_reference(name, golden_dir):
-    """CrossFormer_partseg + CrossEntropyLoss(label_smoothing=0.2): oracle restatement vs vectors from the REAL reference."""
+    """CrossFormer_partseg + CrossEntropyLoss(label_smoothing=0.2): oracle restatement vs vectors from the REAL reference.
+    `seg_small_dpr`: max_dpr = 0.45 -- the reference's Residual applies DropPath to the WHOLE sum dropout(f(x)) + x
+    (partseg.py:212); the fixture ran the reference's own Residual.forward with pinned per-sample draws."""
     cfg = _synth.SEG_CASES[name]
     g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
     torch.set_num_threads(8)
-    o = oracle_seg_run(cfg)
+    o = oracle_seg_run(cfg, drop=seg_dpr_drop(cfg) if cfg.get("max_dpr", 0.0) > 0 else None)
     gl = torch.from_numpy(g["logits"].astype(np.float32))
     assert _rel(o["logits"], gl) < (1e-3 if g["logits"].dtype == np.float16 else 1e-4)
     assert abs(o["loss"] - float(g["loss"][0])) < 1e-4
     gnames = list(g["grad_names"])
     assert set(gnames) == {k for k in o["names"] if o["sd"][k].grad is not None}
+    if cfg.get("max_dpr", 0.0) > 0:      # the draws must matter: without them the oracle is far from the fixture
+        assert _rel(oracle_seg_run(cfg)["logits"], gl) > 5e-2
     norms = {k: o["sd"][k].grad.double().norm().item() for k in gnames}
     ref = dict(zip(gnames, g["grad_norms"]))
     mx = max(ref.values())

@@ -214,3 +214,58 @@ def test_partseg_guards_and_four_taps():
         model(pts[:, :100].contiguous().cuda(), onehot.cuda())
     with pytest.raises(ValueError):
         _synth.build_seg_model(dict(cfg, layer_idx=[9])).cuda()(pts.cuda(), onehot.cuda())
+
+
+def test_partseg_droppath_matches_oracle_injection(golden_dir):
+    """max_dpr = 0.45 (DropPath on, partseg.py:206,212; the reference's own default for this model is 0.1): the product's
+    per-sample scales (vpf_droppath_scales, bit-exact vs oracle/rng.py) are injected into the oracle, which
+    tests/test_oracle_model_golden.py pins to the reference's Residual.forward for this configuration."""
+    import oracle.rng as R
+    import vipformer_b200.runtime as rt
+    from test_oracle_model_golden import seg_dpr_drop
+    from vipformer_b200 import ops
+    from vipformer_b200.loss import CrossEntropyLoss
+
+    cfg = _synth.SEG_CASES["seg_small_dpr"]
+    # the scale kernel itself: integer decisions, bit-exact
+    seed = torch.tensor([_synth.DPR_SEED], device="cuda", dtype=torch.int64)
+    for op_id, p in ((27, 0.15), (28, 0.45), (1234567, 0.3)):
+        s = ops.droppath_scales(seed, op_id, p, 64, seed).cpu().numpy()
+        ref = R.droppath_scales(_synth.DPR_SEED, op_id, p, 64)
+        assert np.array_equal(s > 0, ref > 0), (op_id, p)            # the keep decisions: integer work, exact
+        assert np.array_equal(s, ref), (op_id, p, s.max(), ref.max())   # and the fp32 scale 1 / (1 - p)
+    x = torch.randn((6 * 7, 128), device="cuda")
+    sc = torch.tensor([0.0, 2.0, 1.5, 0.0, 1.0, 3.0], device="cuda")
+    assert torch.equal(ops.row_scale(x, sc, 7), x * sc.repeat_interleave(7)[:, None])
+    # model level
+    o0 = oracle_seg_run(cfg, drop=seg_dpr_drop(cfg))
+    model = _synth.build_seg_model(cfg)
+    model.load_state_dict({k: v.detach() for k, v in o0["sd"].items() if k in model.state_dict()})
+    model = model.cuda().train()
+    model.dp1.p = 0.0
+    pts, start, onehot, labels = o0["inputs"]
+    model.fps_start_idx = torch.from_numpy(start).cuda()
+    rt.manual_seed(5)
+    e0 = rt._EPOCH[0]
+    rt.TAP = {}
+    try:
+        logits = model(pts.cuda(), onehot.cuda())
+        tap = rt.TAP
+    finally:
+        rt.TAP = None
+    loss = CrossEntropyLoss(label_smoothing=0.2)(logits.reshape(-1, cfg["parts"]), labels.cuda().reshape(-1))
+    loss.backward()
+    torch.cuda.synchronize()
+    dev_seed = int(rt.StepState.get(torch.device("cuda", torch.cuda.current_device()))[1].item())
+    ob = {"seg.encoder.cross_attn_1": model.encoder.cross_attn_1._op_base + (e0 + 1) * rt.EPOCH_STRIDE}
+    for i, l in enumerate(model.encoder.sa_layers):
+        ob[f"seg.encoder.sa_layers.{i}"] = l._op_base + (e0 + 1) * rt.EPOCH_STRIDE
+    drop = dict(seed=dev_seed, op_bases=ob, atten_drop=0.0, mlp_drop=0.0, drop_path=_synth.seg_drop_path(cfg))
+    o = oracle_seg_run(cfg, pins=_pins(tap), drop=drop)
+    o_plain = oracle_seg_run(cfg)
+    assert relfro(logits, o_plain["logits"]) > 5e-2          # the per-sample drops matter
+    assert relfro(logits, o["logits"]) < 5e-2, relfro(logits, o["logits"])
+    assert abs(loss.item() - o["loss"]) < 2e-2
+    bad, worst = _compare_grads(model, o, 1.5e-1, share_tol=6.5e-2)
+    print(f"part-seg, DropPath on: worst per-parameter rel-Frobenius gradient error {worst:.4f}")
+    assert not bad, bad

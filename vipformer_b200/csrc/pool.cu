@@ -5,6 +5,7 @@
 //   nn.Linear(3, 64|128) / Conv1d(3, 64, 1)          classifier.py:32  partseg.py:499  utils.py:154
 //   Rearrange 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)'   partseg.py:632
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace vpf {
 
@@ -580,6 +581,26 @@ vecmat_bf16_kernel(const float *__restrict__ v, const bf16 *__restrict__ W, int 
   out[n] += acc;
 }
 
+// DropPath scales of one Residual: s[b] = keep(b) ? 1 / (1 - p) : 0   (one decision per sample, rng.cuh keep_sample)
+__global__ void droppath_scales_kernel(const unsigned long long *__restrict__ seed_ptr, uint32_t op_id, float p, int B,
+                                       float *__restrict__ s) {
+  const int b = blockIdx.x * 128 + threadIdx.x;
+  if (b >= B) return;
+  const uint32_t key = rng::make_key(seed_ptr ? *seed_ptr : 0ull, op_id);
+  s[b] = rng::keep_sample(key, (uint32_t)b, rng::threshold32(p)) ? 1.f / (1.f - p) : 0.f;
+}
+// out[r, :] = x[r, :] * s[r / L]  (fp32 rows of D % 4 == 0 channels; out may alias x): DropPath on a [B*L, D] token matrix
+__global__ void __launch_bounds__(256)
+row_scale_kernel(const float *__restrict__ x, const float *__restrict__ s, int L, float *__restrict__ out, long long T, int D4) {
+  const size_t n = (size_t)T * D4;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float f = s[(i / D4) / L];
+    float4 v = reinterpret_cast<const float4 *>(x)[i];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    reinterpret_cast<float4 *>(out)[i] = v;
+  }
+}
+
 }  // namespace vpf
 
 using namespace vpf;
@@ -615,6 +636,21 @@ int vpf_vecmat_bf16(const float *v, const void *W_bf16, int ldw, int K, int N, f
   if (K == 0 || N == 0) return VPF_OK;
   vecmat_bf16_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(v, (const bf16 *)W_bf16, ldw, K, N, out);
   return check_launch("vecmat_bf16_kernel");
+}
+
+int vpf_droppath_scales(const unsigned long long *seed_ptr, unsigned int op_id, float p, int B, float *scales, void *stream) {
+  VPF_REQUIRE(scales && p >= 0.f && p < 1.f, "droppath_scales: bad arguments (p=%f)", p);
+  if (B == 0) return VPF_OK;
+  droppath_scales_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(seed_ptr, op_id, p, B, scales);
+  return check_launch("droppath_scales_kernel");
+}
+
+int vpf_row_scale(const float *x, const float *scales, int L, float *out, long long T, int D, void *stream) {
+  VPF_REQUIRE(x && scales && out && L >= 1 && D % 4 == 0, "row_scale: bad arguments (L=%d D=%d)", L, D);
+  VPF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "row_scale: pointers must be 16-byte aligned");
+  if (T == 0 || D == 0) return VPF_OK;
+  row_scale_kernel<<<grid_for((size_t)T * (D / 4)), 256, 0, (cudaStream_t)stream>>>(x, scales, L, out, T, D / 4);
+  return check_launch("row_scale_kernel");
 }
 
 int vpf_token_pool_fwd(const float *x, float *out, int *argmax, int B, int L, int D, void *stream) {

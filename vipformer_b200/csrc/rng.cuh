@@ -50,5 +50,16 @@ __device__ __forceinline__ void drop_values(float (&v)[NV], uint32_t key, uint32
   }
 }
 
+
+// ---- DropPath (timm.models.layers.DropPath as used by Residual, partseg.py:201-213): one keep decision per SAMPLE,
+// survivors scaled by 1 / (1 - p).  32-bit threshold: drop iff hash(key, b) < p * 2^32.  Restated in oracle/rng.py.
+__host__ __device__ __forceinline__ uint32_t threshold32(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ bool keep_sample(uint32_t key, uint32_t b, uint32_t thr32) {
+  return mix32(b * 0x9e3779b1u ^ key) >= thr32;
+}
+
 }  // namespace rng
 }  // namespace vpf

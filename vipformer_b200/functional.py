@@ -84,8 +84,16 @@ def sa_layer_fwd(x_prev, pos, W, cfg, seed, op_base, save=True):
     o, lse = ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, L, L, cfg.scale, cfg.p_attn, seed, op_base)
     x1 = _empty((T, D), F32, x_prev)
     ops.gemm(o, W.wo, x1, bias=W.bo, mode=EPI_RESIDUAL, resid=xin, drop_p=cfg.p_res1, seed=seed, op_id=op_base + 1)
+    s1 = s2 = None
+    p_path = getattr(cfg, "p_path", 0.0)
+    if p_path > 0.0:      # DropPath of the attention Residual: the WHOLE sum dropout(f(x)) + x is scaled per sample (partseg.py:212)
+        s1 = ops.droppath_scales(seed, op_base + 3, p_path, B, x1)
+        ops.row_scale(x1, s1, L, out=x1)
     x2, cm = _mlp_fwd(x1, W, T, D, cfg.p_res2, seed, op_base + 2, save)
-    ctx = NS(xn=xn, mean1=mean1, rstd1=rstd1, xin=xin, qkv=qkv, o=o, lse=lse, mlp=cm) if save else None
+    if p_path > 0.0:      # ... and of the MLP Residual, an independent draw
+        s2 = ops.droppath_scales(seed, op_base + 4, p_path, B, x2)
+        ops.row_scale(x2, s2, L, out=x2)
+    ctx = NS(xn=xn, mean1=mean1, rstd1=rstd1, xin=xin, qkv=qkv, o=o, lse=lse, mlp=cm, s1=s1, s2=s2) if save else None
     return x2, ctx
 
 
@@ -94,8 +102,12 @@ def sa_layer_bwd(dx2, c, W, G, cfg, seed, op_base, dpos, g2=None, emit=None):
     The LayerNorm backward of the MLP block emits this layer's own attention-residual operand (g1) the same way."""
     B, L, D, H = cfg.B, cfg.L, cfg.D, cfg.H
     T = B * L
-    dx1, g1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2, g2=g2,
-                       emit=(cfg.p_res1, seed, op_base + 1, G.bo))
+    own_emit = (cfg.p_res1, seed, op_base + 1, G.bo)
+    if c.s2 is not None:      # DropPath: the gradient of the whole Residual output is scaled per sample before it splits
+        dx2, g2, own_emit = ops.row_scale(dx2, c.s2, L), None, None
+    dx1, g1 = _mlp_bwd(dx2, c.mlp, W, G, T, D, cfg.p_res2, seed, op_base + 2, g2=g2, emit=own_emit)
+    if c.s1 is not None:
+        ops.row_scale(dx1, c.s1, L, out=dx1)
     if g1 is None:
         g1 = ops.dropout_grad(dx1, cfg.p_res1, seed, op_base + 1, colsum=G.bo)
     _wgrad(g1, c.o, G.wo)

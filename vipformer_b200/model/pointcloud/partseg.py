@@ -105,11 +105,12 @@ class MLP(Sequential):
 class Residual(nn.Module):
     def __init__(self, module: nn.Module, dropout: float, drop_path_rate: float):
         super().__init__()
-        if drop_path_rate > 0.0:
-            raise NotImplementedError("DropPath (max_dpr > 0) is not implemented: every shipped script uses --max_dpr 0.0")
         self.module = module
         self.dropout = nn.Dropout(p=dropout)
+        # timm's DropPath has no parameters or buffers: an Identity placeholder keeps the state_dict identical; the rate is
+        # applied by the enclosing fused layer (per-sample scales from the device step seed, functional.sa_layer_fwd)
         self.drop_path = nn.Identity()
+        self.drop_path_rate = float(drop_path_rate)
 
     def forward(self, *args, **kwargs):
         _fragment_error("Residual")
@@ -140,6 +141,9 @@ class _LayerBase(Sequential):
     def _p(self, training):
         return (self._p_attn, self._p_res1, self._p_res2) if training else (0.0, 0.0, 0.0)
 
+    def _path(self, training):
+        return float(getattr(self, "_p_path", 0.0)) if training else 0.0
+
 
 class CrossAttentionLayer(_LayerBase):
     def __init__(self, num_heads: int, num_q_input_channels: int, num_kv_input_channels: int,
@@ -154,6 +158,8 @@ class CrossAttentionLayer(_LayerBase):
                                     num_latent_channels=num_latent_channels, dropout=atten_drop)
         super().__init__(Residual(cross_attn, atten_drop, drop_path_rate),
                          Residual(MLP(num_q_input_channels, widening_factor), mlp_drop, drop_path_rate))
+        if drop_path_rate > 0.0:
+            raise NotImplementedError("DropPath on the cross-attention layer is not built (Encoder never sets it, partseg.py:286-295)")
         # partseg.py:165-166: attention residual dropout = atten_drop, MLP residual dropout = mlp_drop
         self._p_attn, self._p_res1, self._p_res2 = atten_drop, atten_drop, mlp_drop
         self._H, self._D = num_heads, num_latent_channels
@@ -199,6 +205,7 @@ class SelfAttentionLayer(_LayerBase):
         super().__init__(Residual(self_attn, mlp_drop, drop_path_rate),
                          Residual(MLP(num_latent_channels, widening_factor), mlp_drop, drop_path_rate))
         self._p_attn, self._p_res1, self._p_res2 = atten_drop, mlp_drop, mlp_drop
+        self._p_path = float(drop_path_rate)          # both Residuals of the layer, independent draws (partseg.py:186-187)
         self._H, self._D = num_heads, num_latent_channels
         self._init_op_base()
 
@@ -222,7 +229,7 @@ class SelfAttentionLayer(_LayerBase):
     def _cfg(self, B, L, Lk=None):
         pa, p1, p2 = self._p(self.training)
         return NS(B=B, L=L, Lk=L, D=self._D, H=self._H, scale=self[0].module.attention.dp_scale, p_attn=pa,
-                  p_res1=p1, p_res2=p2)
+                  p_res1=p1, p_res2=p2, p_path=self._path(self.training))
 
     def forward(self, x, pad_mask=None, attn_mask=None):
         """partseg.py:170-188 applied to x [B,L,D] fp32."""
@@ -326,7 +333,8 @@ class _EncoderFn(torch.autograd.Function):
                 g = None
             else:
                 emit = None
-                if li > 0 and (li - 1) not in tap_grads:       # the layer below consumes dx through its MLP-residual dropout
+                if li > 0 and (li - 1) not in tap_grads and getattr(ctx.ctxs[li - 1][1], "p_path", 0.0) == 0.0:
+                    # the layer below consumes dx through its MLP-residual dropout (unless its DropPath rescales dx first)
                     below, cfg_b, _, op_b = ctx.ctxs[li - 1]
                     emit = (cfg_b.p_res2, ctx.seed, op_b + 2, below._grads().b2)
                 dx, g = Fn.sa_layer_bwd(dx, c, layer._weights(), G, cfg, ctx.seed, op_base, dpos, g2=g, emit=emit)
@@ -657,7 +665,7 @@ class _PartSegHeadFn(torch.autograd.Function):
 
 class CrossFormer_partseg(nn.Module):
     """partseg.py:345-470.  forward(pts [B,N,3], cls_label [B,16]) -> part logits [B, N, num_part_classes].
-    DropPath is not built: construct with max_dpr = 0.0 (the reference's default 0.1 raises here)."""
+    DropPath (max_dpr > 0, the reference's default 0.1) is applied by the fused self-attention layers."""
 
     def __init__(self, input_adapter=None, num_latents=128, num_latent_channels=384, group_size=32,
                  num_cross_attention_layers=1, num_cross_attention_heads=6, num_self_attention_layers=12,

@@ -293,6 +293,21 @@ def group_sum(x, G, S, C, want_bf16=True, want_f32=False):
     return ob, of
 
 
+def droppath_scales(seed, op_id, p, B, like):
+    s = torch.empty(B, dtype=F32, device=like.device)
+    _lib.call("vpf_droppath_scales", _p(seed), _u(op_id), _f(p), _i(B), _p(s), _s())
+    return s
+
+
+def row_scale(x, scales, L, out=None):
+    """out[r, :] = x[r, :] * scales[r // L]   (fp32 [T, D]; out may be x itself)."""
+    T, D = x.shape
+    out = torch.empty_like(x) if out is None else out
+    assert x.dtype == F32 and x.is_contiguous() and out.is_contiguous()
+    _lib.call("vpf_row_scale", _p(x), _p(scales), _i(L), _p(out), _ll(T), _i(D), _s())
+    return out
+
+
 def vecmat_bf16(v, W, out):
     """out[n] += sum_k v[k] * W[k, n];  v fp32 [K], W bf16 [K, N] window (row stride W.stride(0)), out fp32 [N]."""
     K, N = W.shape
